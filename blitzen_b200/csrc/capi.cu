@@ -1,0 +1,639 @@
+// C-ABI layer (include/blz_cull.h): the context that owns the device-side mirror of the reference's shared scene
+// buffers and enqueues the cull kernels.  It plays the role of the backend class's SetupForRendering + the five cull
+// dispatch functions inside DrawFrame (BlitzenVulkan/vulkanRendererSetup.cpp:365-666, vulkanDraw.cpp:107-226, :318-423,
+// :554-622; BlitzenDX12/dx12Draw.cpp:114-413).  No torch types, no CPU fallback.
+#include "ctx.h"
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <new>
+
+namespace blz { void pyramid_plan(PyramidBuildParams& p); void gather_release(blz_cull_ctx* c); }
+using namespace blz;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+} // namespace
+namespace blz {
+int fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_lastError = buf;
+    return code;
+}
+} // namespace blz
+namespace {
+
+
+template <class T> void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+} // namespace
+
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_tiled()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+ViewConsts make_view_consts(const CameraViewData& v)
+{
+    ViewConsts c;
+    for (int col = 0; col < 4; ++col)
+        for (int row = 0; row < 3; ++row) c.m[col * 3 + row] = v.view[col * 4 + row];
+    c.frustumRight = v.frustumRight; c.frustumLeft = v.frustumLeft; c.frustumTop = v.frustumTop; c.frustumBottom = v.frustumBottom;
+    c.proj0 = v.proj0; c.proj5 = v.proj5; c.zNear = v.zNear; c.zFar = v.zFar;
+    c.pyramidWidth = v.pyramidWidth; c.pyramidHeight = v.pyramidHeight; c.lodTarget = v.lodTarget;
+    return c;
+}
+
+int ensure_status(blz_cull_ctx* c, size_t entries)
+{
+    if (entries <= c->statusEntries) return BLZ_OK;
+    dfree(c->status);
+    c->statusEntries = 0;
+    CU_TRY(cudaMalloc(&c->status, entries * sizeof(uint64_t)));
+    CU_TRY(cudaMemsetAsync(c->status, 0, entries * sizeof(uint64_t), c->stream));
+    c->statusEntries = entries;
+    return BLZ_OK;
+}
+
+uint32_t tiles_for(uint64_t n) { return n == 0 ? 1u : uint32_t((n + kCullTile - 1) / kCullTile); }
+
+void pyramid_layout(uint32_t depthW, uint32_t depthH, int variant, PyramidDesc& d, size_t& texels)
+{
+    uint32_t w, h;
+    if (variant == BLZ_HIZ_VK) {
+        // BlitML::PreviousPow2 (BlitzenMathLibrary/blitML.h:54-62): largest power of two r with r*2 < v ... i.e. strictly below v for v > 1
+        auto prev = [](uint32_t v) { uint32_t r = 1; while (r * 2 < v) r *= 2; return r; };
+        w = prev(depthW); h = prev(depthH);
+    } else {
+        w = depthW >> 1 ? depthW >> 1 : 1u; h = depthH >> 1 ? depthH >> 1 : 1u;      // dx12RNDResources.cpp:103-106
+    }
+    uint32_t mips = 0;                                                            // GetDepthPyramidMipLevels, blitML.h:95-107
+    for (uint32_t a = w, b = h; a > 1 || b > 1; a /= 2, b /= 2) ++mips;
+    d.width = w; d.height = h; d.mips = mips;
+    size_t off = 0;
+    for (uint32_t i = 0; i < 16; ++i) {
+        d.offset[i] = uint32_t(off);
+        if (i < mips) off += size_t((w >> i) ? (w >> i) : 1u) * ((h >> i) ? (h >> i) : 1u);
+    }
+    texels = off;
+}
+
+int ensure_pyramid_storage(blz_cull_ctx* c, int variant, uint32_t depthW, uint32_t depthH)
+{
+    PyramidDesc d{}; size_t texels = 0;
+    pyramid_layout(depthW, depthH, variant, d, texels);
+    if (d.mips == 0 || d.mips > 16) return fail(BLZ_ERR_INVALID, "depth %ux%u gives a pyramid with %u mips (need 1..16)", depthW, depthH, d.mips);
+    if (texels > c->pyrTexels) {
+        dfree(c->pyrData);
+        c->pyrTexels = 0;
+        CU_TRY(cudaMalloc(&c->pyrData, texels * sizeof(float)));
+        c->pyrTexels = texels;
+    }
+    d.data = c->pyrData;
+    c->pyr = d;
+    c->pyrVariant = variant;
+    // the backends publish the pyramid extent through the view block (vulkanRendererSetup.cpp:903-904, dx12Draw.cpp:563-564)
+    c->view.pyramidWidth = float(d.width);
+    c->view.pyramidHeight = float(d.height);
+    return BLZ_OK;
+}
+
+int check_list(blz_cull_ctx* c, int list)
+{
+    if (list < 0 || list > 2) return fail(BLZ_ERR_INVALID, "list %d out of range", list);
+    if (!c->surf || !c->lods) return fail(BLZ_ERR_INVALID, "no scene uploaded");
+    if (!c->haveView) return fail(BLZ_ERR_INVALID, "no view set");
+    return BLZ_OK;
+}
+
+int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_t flags)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    int rc = check_list(c, list); if (rc) return rc;
+    if (fmt != BLZ_REC_VK24 && fmt != BLZ_REC_DX32) return fail(BLZ_ERR_INVALID, "record format %d", fmt);
+    if ((pass == PASS_EARLY || pass == PASS_LATE) && list != BLZ_LIST_OPAQUE) return fail(BLZ_ERR_INVALID, "two-phase passes run on the opaque list only");
+    if (pass == PASS_LATE || pass == PASS_TEMPORAL) {
+        if (hiz != BLZ_HIZ_VK && hiz != BLZ_HIZ_DX) return fail(BLZ_ERR_INVALID, "hiz variant %d", hiz);
+        if (!c->pyrData || c->pyrVariant != hiz) return fail(BLZ_ERR_INVALID, "no depth pyramid of variant %d (call build_pyramid / clear_pyramid)", hiz);
+    }
+    CU_TRY(cudaSetDevice(c->device));
+    DrawCullParams p{};
+    p.objs = c->objs[list]; p.n = c->nObjs[list];
+    p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
+    p.visibility = c->vis; p.draws = c->draws; p.counts = c->counts; p.ctl = c->ctl;
+    p.numTiles = tiles_for(p.n);
+    rc = ensure_status(c, p.numTiles); if (rc) return rc;
+    p.status = c->status;
+    p.objectIdBase = list == BLZ_LIST_OPAQUE ? c->objectIdBase : 0u;
+    p.transformIdBase = c->transformIdBase;
+    p.surfaceCount = c->nSurf; p.lodCount = c->nLods;
+    p.recWords = fmt == BLZ_REC_VK24 ? 6u : 8u;
+    p.flags = flags;
+    p.capacity = c->drawCap;
+    p.view = make_view_consts(c->view);
+    p.pyr = c->pyr;
+    CU_TRY(launch_draw_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
+    c->launches++;
+    c->lastRecWords = p.recWords;
+    return BLZ_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int blz_cull_abi_version(void) { return BLZ_CULL_ABI_VERSION; }
+const char* blz_cull_last_error(void) { return g_lastError.c_str(); }
+
+int blz_cull_create(int device, blz_cull_ctx** out)
+{
+    if (!out) return fail(BLZ_ERR_INVALID, "out_ctx is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(BLZ_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(BLZ_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    CU_TRY(cudaSetDevice(device));
+    blz_cull_ctx* c = new (std::nothrow) blz_cull_ctx();
+    if (!c) return fail(BLZ_ERR_INVALID, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { delete c; return fail(BLZ_ERR_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor); }
+    c->numSMs = prop.multiProcessorCount;
+    CU_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+    c->stream = c->ownStream;
+    CU_TRY(cudaMalloc(&c->ctl, sizeof(ScanCtl)));
+    ScanCtl init{ 0u, 0u, 1u, 0u };
+    CU_TRY(cudaMemcpyAsync(c->ctl, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMalloc(&c->counts, 4 * sizeof(uint32_t)));
+    CU_TRY(cudaMemsetAsync(c->counts, 0, 4 * sizeof(uint32_t), c->stream));
+    CU_TRY(cudaMalloc(&c->pyrTicket, sizeof(uint32_t)));
+    CU_TRY(cudaMemsetAsync(c->pyrTicket, 0, sizeof(uint32_t), c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return BLZ_OK;
+}
+
+static void free_scene(blz_cull_ctx* c)
+{
+    for (int i = 0; i < 3; ++i) { dfree(c->objs[i]); c->nObjs[i] = 0; }
+    dfree(c->xfPS); dfree(c->xfQ); dfree(c->xfStage); c->nXf = 0; c->xfStageCap = 0;
+    dfree(c->surf); dfree(c->lods); dfree(c->clusters); dfree(c->lodInst); dfree(c->bucketCap);
+    dfree(c->vis); dfree(c->draws); dfree(c->dispatch); dfree(c->instIdx);
+    c->nSurf = c->nLods = c->nClusters = c->nLodInst = 0; c->drawCap = c->dispatchCap = c->instCap = 0;
+}
+
+int blz_cull_destroy(blz_cull_ctx* c)
+{
+    if (!c) return BLZ_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    dfree(c->ctl); dfree(c->status); dfree(c->counts); dfree(c->depthOwned); dfree(c->pyrData); dfree(c->pyrTicket);
+    blz::gather_release(c);
+    if (c->ownStream) cudaStreamDestroy(c->ownStream);
+    delete c;
+    return BLZ_OK;
+}
+
+int blz_cull_set_stream(blz_cull_ctx* c, void* s)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->ownStream;
+    return BLZ_OK;
+}
+int blz_cull_get_stream(blz_cull_ctx* c, void** out)
+{
+    if (!c || !out) return fail(BLZ_ERR_INVALID, "null argument");
+    *out = c->stream; return BLZ_OK;
+}
+int blz_cull_synchronize(blz_cull_ctx* c)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return BLZ_OK;
+}
+
+int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
+{
+    if (!c || !d) return fail(BLZ_ERR_INVALID, "null argument");
+    if (!d->surfaces || d->surface_count == 0 || !d->lods || d->lod_count == 0) return fail(BLZ_ERR_INVALID, "surfaces and lods are required");
+    if (!d->transforms || d->transform_count == 0) return fail(BLZ_ERR_INVALID, "transforms are required");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    free_scene(c);
+    const cudaMemcpyKind kind = d->inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const void* lists[3] = { d->renders, d->transparent_renders, d->onpc_renders };
+    const uint32_t counts[3] = { d->render_count, d->transparent_count, d->onpc_count };
+    uint64_t maxList = 0;
+    for (int i = 0; i < 3; ++i) {
+        c->nObjs[i] = counts[i];
+        if (counts[i] > maxList) maxList = counts[i];
+        if (counts[i] == 0) continue;
+        if (!lists[i]) return fail(BLZ_ERR_INVALID, "render list %d has a count but no pointer", i);
+        CU_TRY(cudaMalloc(&c->objs[i], size_t(counts[i]) * sizeof(RenderObject)));
+        CU_TRY(cudaMemcpyAsync(c->objs[i], lists[i], size_t(counts[i]) * sizeof(RenderObject), kind, c->stream));
+    }
+    // transforms: AoS staging -> SoA repack (one-time; the per-frame path only reads the SoA streams)
+    c->nXf = d->transform_count;
+    CU_TRY(cudaMalloc(&c->xfPS, size_t(c->nXf) * sizeof(float4)));
+    CU_TRY(cudaMalloc(&c->xfQ, size_t(c->nXf) * sizeof(float4)));
+    {
+        MeshTransform* stage = nullptr;
+        const MeshTransform* src = reinterpret_cast<const MeshTransform*>(d->transforms);
+        if (!d->inputs_on_device) {
+            CU_TRY(cudaMalloc(&stage, size_t(c->nXf) * sizeof(MeshTransform)));
+            CU_TRY(cudaMemcpyAsync(stage, d->transforms, size_t(c->nXf) * sizeof(MeshTransform), cudaMemcpyHostToDevice, c->stream));
+            src = stage;
+        }
+        cudaError_t e = launch_repack_transforms(src, c->xfPS, c->xfQ, 0, c->nXf, c->stream);
+        c->launches++;
+        cudaError_t e2 = cudaStreamSynchronize(c->stream);
+        if (stage) cudaFree(stage);
+        if (e != cudaSuccess) return fail(BLZ_ERR_CUDA, "transform repack launch failed: %s", cudaGetErrorString(e));
+        if (e2 != cudaSuccess) return fail(BLZ_ERR_CUDA, "transform repack failed: %s", cudaGetErrorString(e2));
+    }
+    c->nSurf = d->surface_count; c->nLods = d->lod_count;
+    CU_TRY(cudaMalloc(&c->surf, size_t(c->nSurf) * sizeof(PrimitiveSurface)));
+    CU_TRY(cudaMemcpyAsync(c->surf, d->surfaces, size_t(c->nSurf) * sizeof(PrimitiveSurface), kind, c->stream));
+    CU_TRY(cudaMalloc(&c->lods, size_t(c->nLods) * sizeof(LodData)));
+    CU_TRY(cudaMemcpyAsync(c->lods, d->lods, size_t(c->nLods) * sizeof(LodData), kind, c->stream));
+    if (d->clusters && d->cluster_count) {
+        c->nClusters = d->cluster_count;
+        CU_TRY(cudaMalloc(&c->clusters, size_t(c->nClusters) * sizeof(Cluster)));
+        CU_TRY(cudaMemcpyAsync(c->clusters, d->clusters, size_t(c->nClusters) * sizeof(Cluster), kind, c->stream));
+    }
+    c->objectIdBase = d->object_id_base; c->transformIdBase = d->transform_id_base;
+    // visibility buffer, zero-filled (vulkanRendererSetup.cpp:349)
+    const size_t nVis = c->nObjs[0] ? c->nObjs[0] : 1;
+    CU_TRY(cudaMalloc(&c->vis, nVis * sizeof(uint32_t)));
+    CU_TRY(cudaMemsetAsync(c->vis, 0, nVis * sizeof(uint32_t), c->stream));
+    // draw buffer
+    c->drawCap = d->draw_capacity ? d->draw_capacity : (maxList ? maxList : 1);
+    CU_TRY(cudaMalloc(&c->draws, size_t(c->drawCap) * 8u * sizeof(uint32_t)));
+    // cluster dispatch buffer
+    c->dispatchCap = d->cluster_dispatch_capacity;
+    if (c->dispatchCap) CU_TRY(cudaMalloc(&c->dispatch, size_t(c->dispatchCap) * 3u * sizeof(uint32_t)));
+    // instancing
+    if (d->lod_instances && d->lod_instance_count) {
+        if (d->inputs_on_device && !d->instance_bucket_capacity) return fail(BLZ_ERR_INVALID, "device inputs need explicit instance_bucket_capacity");
+        if (d->lod_instance_count != d->lod_count) return fail(BLZ_ERR_INVALID, "lod_instance_count (%u) must equal lod_count (%u)", d->lod_instance_count, d->lod_count);
+        c->nLodInst = d->lod_instance_count;
+        CU_TRY(cudaMalloc(&c->lodInst, size_t(c->nLodInst) * sizeof(LodInstanceCounter)));
+        CU_TRY(cudaMemcpyAsync(c->lodInst, d->lod_instances, size_t(c->nLodInst) * sizeof(LodInstanceCounter), kind, c->stream));
+        std::vector<uint32_t> cap(c->nLodInst);
+        std::vector<LodInstanceCounter> li(c->nLodInst);
+        if (d->inputs_on_device) CU_TRY(cudaMemcpy(li.data(), d->lod_instances, li.size() * sizeof(LodInstanceCounter), cudaMemcpyDeviceToHost));
+        else memcpy(li.data(), d->lod_instances, li.size() * sizeof(LodInstanceCounter));
+        uint64_t end = 0;
+        for (uint32_t l = 0; l < c->nLodInst; ++l) {
+            if (d->instance_bucket_capacity) {
+                if (d->inputs_on_device) { uint32_t v; CU_TRY(cudaMemcpy(&v, d->instance_bucket_capacity + l, 4, cudaMemcpyDeviceToHost)); cap[l] = v; }
+                else cap[l] = d->instance_bucket_capacity[l];
+            } else {
+                // reference: instanceOffset = lodId * Ce_MaxInstanceCountPerLOD (Resources/Mesh/blitzenMeshes.cpp:159-161, Core/blitzenEngine.h:65)
+                cap[l] = (l + 1 < c->nLodInst && li[l + 1].instanceOffset > li[l].instanceOffset) ? li[l + 1].instanceOffset - li[l].instanceOffset : 100000u;
+            }
+            if (uint64_t(li[l].instanceOffset) + cap[l] > end) end = uint64_t(li[l].instanceOffset) + cap[l];
+        }
+        c->instCap = end ? end : 1;
+        CU_TRY(cudaMalloc(&c->bucketCap, size_t(c->nLodInst) * sizeof(uint32_t)));
+        CU_TRY(cudaMemcpyAsync(c->bucketCap, cap.data(), cap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaMalloc(&c->instIdx, size_t(c->instCap) * sizeof(uint32_t)));
+        CU_TRY(cudaStreamSynchronize(c->stream));   // cap vector leaves scope
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return BLZ_OK;
+}
+
+int blz_cull_update_transforms(blz_cull_ctx* c, uint32_t first, uint32_t count, const void* host)
+{
+    if (!c || (!host && count)) return fail(BLZ_ERR_INVALID, "null argument");
+    if (count == 0) return BLZ_OK;
+    if (first < c->transformIdBase || uint64_t(first - c->transformIdBase) + count > c->nXf)
+        return fail(BLZ_ERR_INVALID, "transform range [%u, %u) outside this context's [%u, %u)", first, first + count, c->transformIdBase, c->transformIdBase + c->nXf);
+    CU_TRY(cudaSetDevice(c->device));
+    if (count > c->xfStageCap) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        dfree(c->xfStage);
+        CU_TRY(cudaMalloc(&c->xfStage, size_t(count) * sizeof(MeshTransform)));
+        c->xfStageCap = count;
+    }
+    CU_TRY(cudaMemcpyAsync(c->xfStage, host, size_t(count) * sizeof(MeshTransform), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(launch_repack_transforms(c->xfStage, c->xfPS, c->xfQ, first - c->transformIdBase, count, c->stream));
+    c->launches++;
+    return BLZ_OK;
+}
+
+int blz_cull_set_view(blz_cull_ctx* c, const void* v)
+{
+    if (!c || !v) return fail(BLZ_ERR_INVALID, "null argument");
+    memcpy(&c->view, v, sizeof(CameraViewData));
+    if (c->pyrData) { c->view.pyramidWidth = float(c->pyr.width); c->view.pyramidHeight = float(c->pyr.height); }
+    c->haveView = true;
+    return BLZ_OK;
+}
+
+int blz_cull_reset_visibility(blz_cull_ctx* c)
+{
+    if (!c || !c->vis) return fail(BLZ_ERR_INVALID, "no scene uploaded");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaMemsetAsync(c->vis, 0, size_t(c->nObjs[0] ? c->nObjs[0] : 1) * sizeof(uint32_t), c->stream));
+    return BLZ_OK;
+}
+
+int blz_cull_write_visibility(blz_cull_ctx* c, const uint32_t* host)
+{
+    if (!c || !c->vis || !host) return fail(BLZ_ERR_INVALID, "no scene uploaded / null pointer");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaMemcpyAsync(c->vis, host, size_t(c->nObjs[0]) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return BLZ_OK;
+}
+
+int blz_cull_set_depth(blz_cull_ctx* c, const float* host, uint32_t w, uint32_t h)
+{
+    if (!c || !host || w == 0 || h == 0) return fail(BLZ_ERR_INVALID, "bad depth image");
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t texels = size_t(w) * h;
+    if (texels > c->depthOwnedTexels) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        dfree(c->depthOwned); c->depthOwnedTexels = 0;
+        CU_TRY(cudaMalloc(&c->depthOwned, texels * sizeof(float)));
+        c->depthOwnedTexels = texels;
+    }
+    CU_TRY(cudaMemcpyAsync(c->depthOwned, host, texels * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    c->depth = c->depthOwned; c->depthW = w; c->depthH = h;
+    return BLZ_OK;
+}
+
+int blz_cull_set_depth_device(blz_cull_ctx* c, const float* dev, uint32_t w, uint32_t h)
+{
+    if (!c || !dev || w == 0 || h == 0) return fail(BLZ_ERR_INVALID, "bad depth image");
+    c->depth = dev; c->depthW = w; c->depthH = h;
+    return BLZ_OK;
+}
+
+int blz_cull_build_pyramid(blz_cull_ctx* c, int variant)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    if (variant != BLZ_HIZ_VK && variant != BLZ_HIZ_DX) return fail(BLZ_ERR_INVALID, "hiz variant %d", variant);
+    if (!c->depth) return fail(BLZ_ERR_INVALID, "no depth image set");
+    CU_TRY(cudaSetDevice(c->device));
+    int rc = ensure_pyramid_storage(c, variant, c->depthW, c->depthH); if (rc) return rc;
+    PyramidBuildParams p{};
+    p.depth = c->depth; p.depthW = c->depthW; p.depthH = c->depthH;
+    p.out = c->pyrData; p.width = c->pyr.width; p.height = c->pyr.height; p.mips = c->pyr.mips;
+    memcpy(p.offset, c->pyr.offset, sizeof(p.offset));
+    p.ticket = c->pyrTicket;
+    p.variant = variant == BLZ_HIZ_VK ? HIZ_VK : HIZ_DX;
+    pyramid_plan(p);
+    CUtensorMap map; const void* mapPtr = nullptr;
+    if (c->optPyramidTma && (c->depthW % 4u) == 0 && (reinterpret_cast<uintptr_t>(c->depth) % 16u) == 0 && p.boxW <= 256 && p.boxH <= 256) {
+        PFN_encodeTiled enc = get_encode_tiled();
+        if (enc) {
+            cuuint64_t gdim[2] = { c->depthW, c->depthH };
+            cuuint64_t gstr[1] = { cuuint64_t(c->depthW) * 4u };
+            cuuint32_t box[2] = { p.boxW, p.boxH };
+            cuuint32_t estr[2] = { 1, 1 };
+            CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(c->depth), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS) mapPtr = &map;
+        }
+    }
+    CU_TRY(launch_pyramid_build(p, mapPtr, c->stream));
+    c->launches++;
+    return BLZ_OK;
+}
+
+int blz_cull_clear_pyramid(blz_cull_ctx* c, int variant, uint32_t w, uint32_t h)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    if (variant != BLZ_HIZ_VK && variant != BLZ_HIZ_DX) return fail(BLZ_ERR_INVALID, "hiz variant %d", variant);
+    CU_TRY(cudaSetDevice(c->device));
+    int rc = ensure_pyramid_storage(c, variant, w, h); if (rc) return rc;
+    CU_TRY(cudaMemsetAsync(c->pyrData, 0, c->pyrTexels * sizeof(float), c->stream));
+    return BLZ_OK;
+}
+
+int blz_cull_frustum_lod(blz_cull_ctx* c, int list, int fmt, uint32_t flags) { return run_draw_pass(c, PASS_FRUSTUM, list, fmt, BLZ_HIZ_VK, flags); }
+int blz_cull_early(blz_cull_ctx* c, int fmt) { return run_draw_pass(c, PASS_EARLY, BLZ_LIST_OPAQUE, fmt, BLZ_HIZ_VK, 0); }
+int blz_cull_late(blz_cull_ctx* c, int fmt, int hiz) { return run_draw_pass(c, PASS_LATE, BLZ_LIST_OPAQUE, fmt, hiz, 0); }
+int blz_cull_temporal(blz_cull_ctx* c, int list, int fmt, int hiz) { return run_draw_pass(c, PASS_TEMPORAL, list, fmt, hiz, 0); }
+
+int blz_cull_instanced(blz_cull_ctx* c, int list)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    int rc = check_list(c, list); if (rc) return rc;
+    if (!c->lodInst) return fail(BLZ_ERR_INVALID, "scene was uploaded without lod_instances");
+    if (c->nLods > 256) return fail(BLZ_ERR_CAPACITY, "instancing supports at most 256 LODs (scene has %u)", c->nLods);
+    CU_TRY(cudaSetDevice(c->device));
+    InstanceCullParams p{};
+    p.objs = c->objs[list]; p.n = c->nObjs[list]; p.numTiles = tiles_for(p.n);
+    p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
+    p.lodInstances = c->lodInst; p.bucketCapacity = c->bucketCap; p.instanceIndices = c->instIdx;
+    p.cmds = c->draws; p.counts = c->counts; p.ctl = c->ctl;
+    rc = ensure_status(c, size_t(p.numTiles) * c->nLods); if (rc) return rc;
+    p.status = c->status;
+    p.objectIdBase = list == BLZ_LIST_OPAQUE ? c->objectIdBase : 0u; p.transformIdBase = c->transformIdBase;
+    p.surfaceCount = c->nSurf; p.lodCount = c->nLods; p.cmdCapacity = c->drawCap;
+    p.view = make_view_consts(c->view);
+    CU_TRY(launch_instance_cull(p, c->numSMs, c->stream));
+    c->launches++;
+    c->lastRecWords = 8u;
+    return BLZ_OK;
+}
+
+int blz_cull_cluster_expand(blz_cull_ctx* c, int list)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    int rc = check_list(c, list); if (rc) return rc;
+    if (!c->dispatch) return fail(BLZ_ERR_INVALID, "scene was uploaded with cluster_dispatch_capacity = 0");
+    CU_TRY(cudaSetDevice(c->device));
+    ClusterExpandParams p{};
+    p.objs = c->objs[list]; p.n = c->nObjs[list]; p.numTiles = tiles_for(p.n);
+    p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
+    p.dispatch = c->dispatch; p.counts = c->counts + 2; p.ctl = c->ctl;
+    rc = ensure_status(c, p.numTiles); if (rc) return rc;
+    p.status = c->status;
+    p.objectIdBase = list == BLZ_LIST_OPAQUE ? c->objectIdBase : 0u; p.transformIdBase = c->transformIdBase;
+    p.surfaceCount = c->nSurf; p.lodCount = c->nLods; p.capacity = c->dispatchCap;
+    p.view = make_view_consts(c->view);
+    CU_TRY(launch_cluster_expand(p, c->numSMs, c->stream));
+    c->launches++;
+    return BLZ_OK;
+}
+
+int blz_cull_cluster_cull(blz_cull_ctx* c, int mode, int fmt, int hiz)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    if (!c->dispatch) return fail(BLZ_ERR_INVALID, "scene was uploaded with cluster_dispatch_capacity = 0");
+    if (!c->clusters) return fail(BLZ_ERR_INVALID, "scene has no clusters");
+    if (mode < 0 || mode > 2) return fail(BLZ_ERR_INVALID, "cluster mode %d", mode);
+    if (fmt != BLZ_REC_VK24 && fmt != BLZ_REC_DX32) return fail(BLZ_ERR_INVALID, "record format %d", fmt);
+    if (mode != BLZ_CLUSTER_PASSTHROUGH && !c->haveView) return fail(BLZ_ERR_INVALID, "no view set");
+    if (mode == BLZ_CLUSTER_SPHERE_HIZ && (!c->pyrData || c->pyrVariant != hiz)) return fail(BLZ_ERR_INVALID, "no depth pyramid of variant %d", hiz);
+    CU_TRY(cudaSetDevice(c->device));
+    ClusterCullParams p{};
+    p.dispatch = c->dispatch; p.dispatchCount = c->counts + 2;
+    p.objs = c->objs[BLZ_LIST_OPAQUE]; p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.clusters = c->clusters;
+    p.draws = c->draws; p.counts = c->counts; p.ctl = c->ctl;
+    p.maxRecords = uint32_t(c->dispatchCap > 0xFFFFFFFFull ? 0xFFFFFFFFull : c->dispatchCap);
+    int rc = ensure_status(c, tiles_for(p.maxRecords)); if (rc) return rc;
+    p.status = c->status;
+    p.objectIdBase = c->objectIdBase; p.transformIdBase = c->transformIdBase; p.clusterCount = c->nClusters;
+    p.recWords = fmt == BLZ_REC_VK24 ? 6u : 8u; p.mode = uint32_t(mode); p.capacity = c->drawCap;
+    p.view = make_view_consts(c->view); p.pyr = c->pyr;
+    CU_TRY(launch_cluster_cull(p, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
+    c->launches++;
+    c->lastRecWords = p.recWords;
+    return BLZ_OK;
+}
+
+int blz_cull_set_cluster_dispatch(blz_cull_ctx* c, const void* records, uint64_t count, int onDevice)
+{
+    if (!c || (!records && count)) return fail(BLZ_ERR_INVALID, "null argument");
+    if (!c->dispatch || count > c->dispatchCap) return fail(BLZ_ERR_CAPACITY, "dispatch list of %llu records exceeds capacity %llu", (unsigned long long)count, (unsigned long long)c->dispatchCap);
+    CU_TRY(cudaSetDevice(c->device));
+    if (count) CU_TRY(cudaMemcpyAsync(c->dispatch, records, size_t(count) * 12u, onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    uint32_t cnt[2] = { uint32_t(count), uint32_t(count) };
+    CU_TRY(cudaMemcpyAsync(c->counts + 2, cnt, sizeof(cnt), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return BLZ_OK;
+}
+
+int blz_cull_get_outputs(blz_cull_ctx* c, blz_outputs* o)
+{
+    if (!c || !o) return fail(BLZ_ERR_INVALID, "null argument");
+    memset(o, 0, sizeof(*o));
+    o->draws = c->draws; o->draw_count = c->counts; o->visibility = c->vis;
+    o->cluster_dispatch = c->dispatch; o->cluster_count = c->counts ? c->counts + 2 : nullptr;
+    o->instance_indices = c->instIdx; o->instance_counts = reinterpret_cast<uint32_t*>(c->lodInst);
+    o->pyramid = c->pyrData; o->pyramid_width = c->pyr.width; o->pyramid_height = c->pyr.height; o->pyramid_mips = c->pyr.mips;
+    memcpy(o->pyramid_offset, c->pyr.offset, sizeof(o->pyramid_offset));
+    o->draw_capacity = c->drawCap; o->cluster_dispatch_capacity = c->dispatchCap;
+    return BLZ_OK;
+}
+
+int blz_cull_read_count(blz_cull_ctx* c, uint32_t* written, uint32_t* total)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    CU_TRY(cudaSetDevice(c->device));
+    uint32_t h[2];
+    CU_TRY(cudaMemcpyAsync(h, c->counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (written) *written = h[0];
+    if (total) *total = h[1];
+    return BLZ_OK;
+}
+
+static int read_records(blz_cull_ctx* c, const uint32_t* dev, const uint32_t* devCounts, uint32_t recWords, void* host, uint64_t cap, uint32_t* written, uint32_t* total)
+{
+    CU_TRY(cudaSetDevice(c->device));
+    uint32_t h[2];
+    CU_TRY(cudaMemcpyAsync(h, devCounts, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (written) *written = h[0];
+    if (total) *total = h[1];
+    if (host) {
+        uint64_t n = h[0] < cap ? h[0] : cap;
+        if (n) {
+            CU_TRY(cudaMemcpyAsync(host, dev, size_t(n) * recWords * 4u, cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(cudaStreamSynchronize(c->stream));
+        }
+    }
+    return BLZ_OK;
+}
+
+// capacity_records counts records of the format the last pass wrote (VK24 or DX32)
+int blz_cull_read_draws(blz_cull_ctx* c, void* host, uint64_t cap, uint32_t* written, uint32_t* total)
+{
+    if (!c || !c->draws) return fail(BLZ_ERR_INVALID, "no scene uploaded");
+    return read_records(c, c->draws, c->counts, c->lastRecWords, host, cap, written, total);
+}
+
+int blz_cull_read_visibility(blz_cull_ctx* c, uint32_t* host)
+{
+    if (!c || !c->vis || !host) return fail(BLZ_ERR_INVALID, "no scene uploaded / null pointer");
+    CU_TRY(cudaSetDevice(c->device));
+    if (c->nObjs[0]) CU_TRY(cudaMemcpyAsync(host, c->vis, size_t(c->nObjs[0]) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return BLZ_OK;
+}
+
+int blz_cull_read_cluster_dispatch(blz_cull_ctx* c, void* host, uint64_t cap, uint32_t* written, uint32_t* total)
+{
+    if (!c || !c->dispatch) return fail(BLZ_ERR_INVALID, "cluster path not enabled");
+    return read_records(c, c->dispatch, c->counts + 2, 3u, host, cap, written, total);
+}
+
+int blz_cull_read_instances(blz_cull_ctx* c, uint32_t* idxHost, uint64_t cap, void* countersHost)
+{
+    if (!c || !c->lodInst) return fail(BLZ_ERR_INVALID, "instancing not enabled");
+    CU_TRY(cudaSetDevice(c->device));
+    if (idxHost) {
+        uint64_t n = c->instCap < cap ? c->instCap : cap;
+        if (n) CU_TRY(cudaMemcpyAsync(idxHost, c->instIdx, size_t(n) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (countersHost) CU_TRY(cudaMemcpyAsync(countersHost, c->lodInst, size_t(c->nLodInst) * sizeof(LodInstanceCounter), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return BLZ_OK;
+}
+
+int blz_cull_read_pyramid(blz_cull_ctx* c, float* host, uint64_t cap, uint32_t* whm, uint32_t* offsets)
+{
+    if (!c || !c->pyrData) return fail(BLZ_ERR_INVALID, "no pyramid");
+    CU_TRY(cudaSetDevice(c->device));
+    size_t texels = 0; PyramidDesc d{};
+    d = c->pyr;
+    for (uint32_t i = 0; i < d.mips; ++i) texels += size_t((d.width >> i) ? (d.width >> i) : 1u) * ((d.height >> i) ? (d.height >> i) : 1u);
+    if (whm) { whm[0] = d.width; whm[1] = d.height; whm[2] = d.mips; }
+    if (offsets) memcpy(offsets, d.offset, sizeof(d.offset));
+    if (host) {
+        if (cap < texels) return fail(BLZ_ERR_CAPACITY, "pyramid has %zu texels, buffer holds %llu", texels, (unsigned long long)cap);
+        CU_TRY(cudaMemcpyAsync(host, c->pyrData, texels * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return BLZ_OK;
+}
+
+int blz_cull_launch_count(blz_cull_ctx* c, uint64_t* out)
+{
+    if (!c || !out) return fail(BLZ_ERR_INVALID, "null argument");
+    *out = c->launches; return BLZ_OK;
+}
+
+int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
+{
+    if (!c || !name) return fail(BLZ_ERR_INVALID, "null argument");
+    if (strcmp(name, "pyramid_tma") == 0) { c->optPyramidTma = value; return BLZ_OK; }
+    return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);
+}
+
+} // extern "C"

@@ -1,0 +1,55 @@
+// Private: the context behind the opaque blz_cull_ctx handle, shared by capi.cu and gather.cu.
+#pragma once
+#include "../../include/blz_cull.h"
+#include "cull_kernels.cuh"
+#include <string>
+
+struct blz_cull_ctx {
+    int device = 0, numSMs = 0;
+    cudaStream_t stream = nullptr, ownStream = nullptr;
+    // scene (device)
+    blz::RenderObject* objs[3] = { nullptr, nullptr, nullptr };
+    uint32_t nObjs[3] = { 0, 0, 0 };
+    float4 *xfPS = nullptr, *xfQ = nullptr; uint32_t nXf = 0;
+    blz::MeshTransform* xfStage = nullptr; uint32_t xfStageCap = 0;
+    blz::PrimitiveSurface* surf = nullptr; uint32_t nSurf = 0;
+    blz::LodData* lods = nullptr; uint32_t nLods = 0;
+    blz::Cluster* clusters = nullptr; uint32_t nClusters = 0;
+    blz::LodInstanceCounter* lodInst = nullptr; uint32_t nLodInst = 0;
+    uint32_t* bucketCap = nullptr;
+    uint32_t objectIdBase = 0, transformIdBase = 0;
+    // per-object state + outputs
+    uint32_t* vis = nullptr;
+    uint32_t* draws = nullptr; uint64_t drawCap = 0;
+    uint32_t* counts = nullptr;               // [0..1] draws, [2..3] cluster dispatch
+    uint32_t* dispatch = nullptr; uint64_t dispatchCap = 0;
+    uint32_t* instIdx = nullptr; uint64_t instCap = 0;
+    blz::ScanCtl* ctl = nullptr;
+    uint64_t* status = nullptr; size_t statusEntries = 0;
+    // depth + pyramid
+    const float* depth = nullptr; float* depthOwned = nullptr; size_t depthOwnedTexels = 0;
+    uint32_t depthW = 0, depthH = 0;
+    float* pyrData = nullptr; size_t pyrTexels = 0;
+    blz::PyramidDesc pyr{};
+    int pyrVariant = -1;
+    uint32_t* pyrTicket = nullptr;
+    // view
+    blz::CameraViewData view{}; bool haveView = false;
+    uint64_t launches = 0;
+    int64_t optPyramidTma = 1;
+    uint32_t lastRecWords = 6;                // record width (u32 words) of the pass that last wrote `draws`
+    // gather (multi-GPU): the presenter owns gatherBuf/gatherFlags; every rank (presenter included) writes through gatherDst*
+    uint32_t* gatherBuf = nullptr; uint64_t gatherCap = 0; uint32_t gatherRecWords = 6; uint64_t* gatherFlags = nullptr; bool gatherOwner = false;
+    uint32_t* gatherDst = nullptr; uint64_t* gatherDstFlags = nullptr; int rank = 0, world = 1; bool gatherImported = false, gatherPeerMapped = false;
+    uint32_t* gatherDone = nullptr;
+};
+
+namespace blz {
+int fail(int code, const char* fmt, ...);
+}
+
+#define CU_TRY(expr)                                                                                          \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess) return blz::fail(BLZ_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)

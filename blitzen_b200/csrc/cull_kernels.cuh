@@ -1,0 +1,98 @@
+// Kernel parameter blocks + launch prototypes shared between the kernels and the C-ABI layer.
+#pragma once
+#include "cull_types.cuh"
+
+namespace blz {
+
+constexpr int kCullThreads = 256;                    // 8 warps per CTA
+constexpr int kCullItems = 4;                        // objects per thread
+constexpr int kCullTile = kCullThreads * kCullItems; // objects per tile (one ticket)
+
+struct DrawCullParams {
+    // inputs
+    const RenderObject* objs;        // AoS, 8 B, the reference layout (two u32)
+    const float4* xfPosScale;        // SoA repack of MeshTransform: {pos.xyz, scale}
+    const float4* xfQuat;            // SoA repack of MeshTransform: orientation
+    const PrimitiveSurface* surfaces;
+    const LodData* lods;
+    uint32_t* visibility;            // u32 per object (early: read, late: read + write)
+    // outputs
+    uint32_t* draws;                 // records, recWords u32 each
+    uint32_t* counts;                // [0] = written (clamped to capacity), [1] = total
+    // scan state
+    ScanCtl* ctl;
+    uint64_t* status;
+    // sizes
+    uint32_t n;                      // objects in the list
+    uint32_t numTiles;               // ceil(n / kCullTile), at least 1
+    uint32_t objectIdBase, transformIdBase;
+    uint32_t surfaceCount, lodCount;
+    uint32_t recWords;               // 6 (VK24) or 8 (DX32)
+    uint32_t flags;
+    uint64_t capacity;               // records
+    ViewConsts view;
+    PyramidDesc pyr;
+};
+
+struct InstanceCullParams {
+    const RenderObject* objs; const float4* xfPosScale; const float4* xfQuat;
+    const PrimitiveSurface* surfaces; const LodData* lods;
+    LodInstanceCounter* lodInstances;     // instanceOffset read, instanceCount written (total survivors of the LOD)
+    const uint32_t* bucketCapacity;       // per LOD
+    uint32_t* instanceIndices;
+    uint32_t* cmds;                       // DX32 records
+    uint32_t* counts;                     // [0] = written cmds, [1] = total cmds
+    ScanCtl* ctl; uint64_t* status;       // status[tile * lodCount + lod]
+    uint32_t n, numTiles, objectIdBase, transformIdBase, surfaceCount, lodCount;
+    uint64_t cmdCapacity;
+    ViewConsts view;
+};
+
+struct ClusterExpandParams {
+    const RenderObject* objs; const float4* xfPosScale; const float4* xfQuat;
+    const PrimitiveSurface* surfaces; const LodData* lods;
+    uint32_t* dispatch;                   // ClusterDispatchData records (3 u32)
+    uint32_t* counts;                     // [0] = written, [1] = total
+    ScanCtl* ctl; uint64_t* status;
+    uint32_t n, numTiles, objectIdBase, transformIdBase, surfaceCount, lodCount;
+    uint64_t capacity;
+    ViewConsts view;
+};
+
+struct ClusterCullParams {
+    const uint32_t* dispatch;             // ClusterDispatchData records
+    const uint32_t* dispatchCount;        // device: [0] = number of records (stays on the device)
+    const RenderObject* objs; const float4* xfPosScale; const float4* xfQuat;
+    const Cluster* clusters;
+    uint32_t* draws; uint32_t* counts;
+    ScanCtl* ctl; uint64_t* status;
+    uint32_t maxRecords;                  // capacity of the dispatch buffer (upper bound of *dispatchCount)
+    uint32_t objectIdBase, transformIdBase, clusterCount;
+    uint32_t recWords, mode;
+    uint64_t capacity;
+    ViewConsts view;
+    PyramidDesc pyr;
+};
+
+// launchers (return the cudaError_t of the launch)
+cudaError_t launch_draw_cull(const DrawCullParams& p, int pass, int hiz, int numSMs, cudaStream_t stream);
+cudaError_t launch_instance_cull(const InstanceCullParams& p, int numSMs, cudaStream_t stream);
+cudaError_t launch_cluster_expand(const ClusterExpandParams& p, int numSMs, cudaStream_t stream);
+cudaError_t launch_cluster_cull(const ClusterCullParams& p, int hiz, int numSMs, cudaStream_t stream);
+cudaError_t launch_repack_transforms(const MeshTransform* aos, float4* posScale, float4* quat, uint32_t first, uint32_t count, cudaStream_t stream);
+
+struct PyramidBuildParams {
+    const float* depth; uint32_t depthW, depthH;
+    float* out;                        // mip chain
+    uint32_t width, height, mips;      // level-0 extent
+    uint32_t offset[16];
+    uint32_t* ticket;                  // device counter, self-resetting
+    uint32_t tilesX, tilesY;
+    uint32_t tileLevels;               // levels produced inside the tile stage (<= 6)
+    uint32_t boxW, boxH;               // input box staged per tile (texels)
+    int variant;
+};
+cudaError_t launch_pyramid_build(const PyramidBuildParams& p, const void* tensorMap /* CUtensorMap* on host or null */, cudaStream_t stream);
+size_t pyramid_smem_bytes(const PyramidBuildParams& p);
+
+} // namespace blz

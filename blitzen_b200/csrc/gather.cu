@@ -1,0 +1,197 @@
+// Multi-GPU draw-list gather (new: the reference is single-GPU).
+// Each rank culls + compacts its shard of the object list into its own draw buffer.  One kernel per rank then
+//   1. publishes the rank's survivor count to the presenting GPU's flag block (one 64-bit peer store over NVLink),
+//   2. waits for the counts of all lower ranks (the exclusive scan of <= 8 counts, done in-kernel),
+//   3. stores its records into the presenter's gather buffer at that offset with peer stores,
+//   4. raises its done flag on the presenter.
+// Concatenation in shard order == ascending global objectId, so the gathered list is byte-identical to the 1-GPU list.
+// No NCCL call and no host round trip on the data path; NCCL (torch.distributed) only carries the 128-byte IPC handle
+// blob at set-up time (blitzen_b200/dist.py).
+#include "ctx.h"
+#include <cstring>
+
+namespace blz {
+
+namespace {
+
+constexpr int kGatherThreads = 256;
+constexpr int kFlagStride = 64;      // count words at [0, 64), done words at [64, 128)
+
+__device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct GatherParams {
+    const uint32_t* src; const uint32_t* srcCount;   // this rank's compacted list (device-local)
+    uint32_t* dst; uint64_t* flags;                  // presenter's buffer + flag block (peer-mapped, or local on the presenter)
+    uint32_t* done;                                  // local CTA-completion counter (self-resetting)
+    uint64_t capacity;                               // records the presenter's buffer holds
+    uint32_t recWords, rank, epoch;
+};
+
+__global__ void __launch_bounds__(kGatherThreads) gather_push_kernel(const GatherParams p)
+{
+    __shared__ uint64_t s_off;
+    const uint32_t tid = threadIdx.x;
+    uint32_t count;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(count) : "l"(p.srcCount));
+    if (tid == 0) {
+        if (blockIdx.x == 0) st_release_sys_u64(p.flags + p.rank, (uint64_t(p.epoch) << 32) | count);
+        uint64_t off = 0;
+        for (uint32_t r = 0; r < p.rank; ++r) {
+            uint64_t w;
+            do { w = ld_acquire_sys_u64(p.flags + r); } while (uint32_t(w >> 32) != p.epoch);
+            off += uint32_t(w);
+        }
+        s_off = off;
+    }
+    __syncthreads();
+    const uint64_t off = s_off;
+    const uint64_t room = off < p.capacity ? p.capacity - off : 0ull;
+    const uint64_t nrec = room < count ? room : count;
+    const uint64_t n64 = nrec * (p.recWords >> 1);
+    const uint2* src = reinterpret_cast<const uint2*>(p.src);
+    uint2* dst = reinterpret_cast<uint2*>(p.dst + off * p.recWords);
+    for (uint64_t j = uint64_t(blockIdx.x) * kGatherThreads + tid; j < n64; j += uint64_t(gridDim.x) * kGatherThreads) dst[j] = src[j];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t prev = atomicAdd(p.done, 1u);
+        if (prev == gridDim.x - 1u) {
+            *p.done = 0u;
+            st_release_sys_u64(p.flags + kFlagStride + p.rank, uint64_t(p.epoch));
+        }
+    }
+}
+
+__global__ void gather_wait_kernel(const uint64_t* flags, uint32_t world, uint32_t epoch)
+{
+    const uint32_t r = threadIdx.x;
+    if (r < world) { while (uint32_t(ld_acquire_sys_u64(flags + kFlagStride + r)) != epoch) { } }
+}
+
+} // namespace
+
+void gather_release(blz_cull_ctx* c)
+{
+    if (c->gatherPeerMapped) {
+        if (c->gatherDst) cudaIpcCloseMemHandle(c->gatherDst);
+        if (c->gatherDstFlags) cudaIpcCloseMemHandle(c->gatherDstFlags);
+    }
+    if (c->gatherOwner) { if (c->gatherBuf) cudaFree(c->gatherBuf); if (c->gatherFlags) cudaFree(c->gatherFlags); }
+    if (c->gatherDone) cudaFree(c->gatherDone);
+    c->gatherBuf = nullptr; c->gatherFlags = nullptr; c->gatherDst = nullptr; c->gatherDstFlags = nullptr; c->gatherDone = nullptr;
+    c->gatherOwner = c->gatherImported = c->gatherPeerMapped = false;
+}
+
+} // namespace blz
+
+using namespace blz;
+
+extern "C" {
+
+int blz_cull_gather_export(blz_cull_ctx* c, uint64_t capacityRecords, int fmt, void* outBlob128)
+{
+    if (!c || !outBlob128 || capacityRecords == 0) return fail(BLZ_ERR_INVALID, "bad argument");
+    if (fmt != BLZ_REC_VK24 && fmt != BLZ_REC_DX32) return fail(BLZ_ERR_INVALID, "record format %d", fmt);
+    CU_TRY(cudaSetDevice(c->device));
+    gather_release(c);
+    c->gatherRecWords = fmt == BLZ_REC_VK24 ? 6u : 8u;
+    c->gatherCap = capacityRecords;
+    CU_TRY(cudaMalloc(&c->gatherBuf, size_t(capacityRecords) * c->gatherRecWords * 4u));
+    CU_TRY(cudaMalloc(&c->gatherFlags, 2 * kFlagStride * sizeof(uint64_t)));
+    CU_TRY(cudaMemset(c->gatherFlags, 0, 2 * kFlagStride * sizeof(uint64_t)));
+    c->gatherOwner = true;
+    cudaIpcMemHandle_t h[2];
+    CU_TRY(cudaIpcGetMemHandle(&h[0], c->gatherBuf));
+    CU_TRY(cudaIpcGetMemHandle(&h[1], c->gatherFlags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    unsigned char* o = static_cast<unsigned char*>(outBlob128);
+    memcpy(o, &h[0], 64); memcpy(o + 64, &h[1], 64);
+    // trailer-free blob: capacity and format travel separately (blitzen_b200/dist.py broadcasts them with the blob)
+    return BLZ_OK;
+}
+
+int blz_cull_gather_import(blz_cull_ctx* c, const void* blob128, int rank, int world)
+{
+    if (!c || rank < 0 || world < 1 || rank >= world || world > kFlagStride) return fail(BLZ_ERR_INVALID, "bad rank/world %d/%d", rank, world);
+    CU_TRY(cudaSetDevice(c->device));
+    c->rank = rank; c->world = world;
+    if (c->gatherOwner) {                       // the presenter writes through its own pointers
+        c->gatherDst = c->gatherBuf; c->gatherDstFlags = c->gatherFlags; c->gatherPeerMapped = false;
+    } else {
+        if (!blob128) return fail(BLZ_ERR_INVALID, "presenter blob is null");
+        cudaIpcMemHandle_t h[2];
+        memcpy(&h[0], blob128, 64); memcpy(&h[1], static_cast<const unsigned char*>(blob128) + 64, 64);
+        void *a = nullptr, *b = nullptr;
+        CU_TRY(cudaIpcOpenMemHandle(&a, h[0], cudaIpcMemLazyEnablePeerAccess));
+        CU_TRY(cudaIpcOpenMemHandle(&b, h[1], cudaIpcMemLazyEnablePeerAccess));
+        c->gatherDst = static_cast<uint32_t*>(a); c->gatherDstFlags = static_cast<uint64_t*>(b); c->gatherPeerMapped = true;
+    }
+    if (!c->gatherDone) {
+        CU_TRY(cudaMalloc(&c->gatherDone, sizeof(uint32_t)));
+        CU_TRY(cudaMemset(c->gatherDone, 0, sizeof(uint32_t)));
+    }
+    c->gatherImported = true;
+    return BLZ_OK;
+}
+
+// capacity/format of the presenter's buffer for ranks that did not export (set by the host layer after the broadcast)
+int blz_cull_gather_configure(blz_cull_ctx* c, uint64_t capacityRecords, int fmt)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    c->gatherCap = capacityRecords; c->gatherRecWords = fmt == BLZ_REC_VK24 ? 6u : 8u;
+    return BLZ_OK;
+}
+
+int blz_cull_gather_push(blz_cull_ctx* c, uint32_t epoch)
+{
+    if (!c || !c->gatherImported) return fail(BLZ_ERR_INVALID, "gather not set up (export/import first)");
+    if (epoch == 0) return fail(BLZ_ERR_INVALID, "epoch must be non-zero and change every push");
+    if (c->lastRecWords != c->gatherRecWords) return fail(BLZ_ERR_INVALID, "last pass wrote %u-word records, gather buffer holds %u-word records", c->lastRecWords, c->gatherRecWords);
+    CU_TRY(cudaSetDevice(c->device));
+    GatherParams p{};
+    p.src = c->draws; p.srcCount = c->counts; p.dst = c->gatherDst; p.flags = c->gatherDstFlags; p.done = c->gatherDone;
+    p.capacity = c->gatherCap; p.recWords = c->gatherRecWords; p.rank = uint32_t(c->rank); p.epoch = epoch;
+    gather_push_kernel<<<c->numSMs * 2, kGatherThreads, 0, c->stream>>>(p);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return BLZ_OK;
+}
+
+int blz_cull_gather_read(blz_cull_ctx* c, uint32_t epoch, void* recordsHost, uint64_t capacityRecords, uint32_t* outCounts)
+{
+    if (!c || !c->gatherOwner) return fail(BLZ_ERR_INVALID, "only the presenting rank (the exporter) can read the gathered list");
+    CU_TRY(cudaSetDevice(c->device));
+    gather_wait_kernel<<<1, kFlagStride, 0, c->stream>>>(c->gatherFlags, uint32_t(c->world), epoch);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    uint64_t flags[kFlagStride];
+    CU_TRY(cudaMemcpyAsync(flags, c->gatherFlags, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    uint64_t total = 0;
+    for (int r = 0; r < c->world; ++r) { if (outCounts) outCounts[r] = uint32_t(flags[r]); total += uint32_t(flags[r]); }
+    if (total > c->gatherCap) total = c->gatherCap;
+    if (recordsHost) {
+        uint64_t n = total < capacityRecords ? total : capacityRecords;
+        if (n) {
+            CU_TRY(cudaMemcpyAsync(recordsHost, c->gatherBuf, size_t(n) * c->gatherRecWords * 4u, cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(cudaStreamSynchronize(c->stream));
+        }
+    }
+    return BLZ_OK;
+}
+
+int blz_cull_gather_outputs(blz_cull_ctx* c, void** outRecords, uint32_t** outFlags)
+{
+    if (!c || !c->gatherOwner) return fail(BLZ_ERR_INVALID, "only the presenting rank owns gather outputs");
+    if (outRecords) *outRecords = c->gatherBuf;
+    if (outFlags) *outFlags = reinterpret_cast<uint32_t*>(c->gatherFlags);
+    return BLZ_OK;
+}
+
+} // extern "C"

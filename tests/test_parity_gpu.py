@@ -1,0 +1,283 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+Bit-exact (draw records, counts, visibility, pyramid texels): integer / byte equality, no tolerance."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import view_at
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi(built):
+    from blitzen_b200 import capi
+    return capi
+
+
+def make_ctx(capi, sc, **kw):
+    ctx = capi.CullContext(0)
+    ctx.upload_scene(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], clusters=sc["clusters"], lod_instances=kw.pop("lod_instances", None), **kw)
+    return ctx
+
+
+def recs_u32(rec):
+    return rec.view(np.uint32).reshape(len(rec), -1)
+
+
+SMALL_VIEWS = {
+    "corner": dict(position=(20, 70, 0), z_far=650.0),
+    "centre": dict(position=(380, 380, 380), z_far=2000.0),
+    "outside_all": dict(position=(380, 380, -2500), z_far=1e9),
+    "tilted": dict(position=(200, 500, 100), yaw=0.7, pitch=-0.3, z_far=900.0),
+    "nothing": dict(position=(380, 380, 5000), z_far=100.0),
+}
+
+
+@pytest.mark.parametrize("vname", list(SMALL_VIEWS))
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_frustum_lod_small(capi, small_scene, vname, fmt):
+    sc = small_scene
+    view = view_at(**SMALL_VIEWS[vname])
+    exp, total, _ = O.cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM, rec_words=6 if fmt == 0 else 8)
+    with make_ctx(capi, sc) as ctx:
+        ctx.set_view(view)
+        ctx.frustum_lod(capi.LIST_OPAQUE, fmt)
+        got, gtotal = ctx.read_draws(fmt)
+    assert gtotal == total
+    assert np.array_equal(recs_u32(got), exp)
+    if vname == "outside_all":
+        assert total == len(sc["objs"])
+    if vname == "nothing":
+        assert total == 0
+
+
+def test_frustum_lod_medium_lookback(capi, medium_scene):
+    sc = medium_scene
+    view = view_at(position=(950, 950, 950), z_far=5000.0)
+    exp, total, _ = O.cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM, threads=8)
+    with make_ctx(capi, sc) as ctx:
+        ctx.set_view(view)
+        for _ in range(3):   # repeated launches reuse the self-resetting control block / epoch-tagged status words
+            ctx.frustum_lod()
+            got, gtotal = ctx.read_draws()
+            assert gtotal == total and total > 100_000
+            assert np.array_equal(recs_u32(got), exp)
+
+
+def test_reference_views_on_reference_head(capi, built, views):
+    """Inputs produced by the reference's own frontend: first 4096 objects of its RenderingStressTest scene, reference camera."""
+    import os
+    from blitzen_b200 import sceneio
+    sc = sceneio.read_blob(os.path.join(os.path.dirname(__file__), "golden", "stress_head_4k.blob"))
+    for name in ("default", "cfg1_centre", "cfg1_all", "cfg1_tilted"):
+        exp, total, _ = O.cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], views[name], O.PASS_FRUSTUM)
+        with capi.CullContext(0) as ctx:
+            ctx.upload_scene(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"])
+            ctx.set_view(views[name])
+            ctx.frustum_lod()
+            got, gtotal = ctx.read_draws()
+        assert gtotal == total
+        assert np.array_equal(recs_u32(got), exp)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("size", [(1920, 1080), (1280, 720), (640, 360), (257, 131), (64, 64), (37, 5), (4, 2)])
+def test_pyramid(capi, built, variant, size):
+    from blitzen_b200 import scene
+    w, h = size
+    depth = scene.synthetic_depth(w, h, n_rects=24, seed=w * 31 + h)
+    rng = np.random.default_rng(w + h)
+    depth += (rng.random((h, w), dtype=np.float32) * np.float32(1e-4))   # break ties so every min has a unique argmin
+    exp = O.build_pyramid(depth, variant)
+    for tma in (1, 0):
+        with capi.CullContext(0) as ctx:
+            ctx.set_option("pyramid_tma", tma)
+            ctx.set_depth(depth)
+            ctx.build_pyramid(variant)
+            ctx.build_pyramid(variant)     # second build re-arms the ticket
+            data, (pw, ph, mips), offs = ctx.read_pyramid()
+        assert (pw, ph, mips) == (exp.width, exp.height, exp.mips)
+        assert list(offs[:mips]) == exp.offsets[:mips]
+        assert np.array_equal(data.view(np.uint32), exp.data[:len(data)].view(np.uint32)), f"pyramid mismatch tma={tma}"
+
+
+@pytest.mark.parametrize("hiz", [0, 1])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_two_phase_frames(capi, small_scene, hiz, fmt):
+    """Frame 0 (visibility all 0, cleared pyramid) then two more frames against a synthetic depth: early + late lists,
+    visibility buffer, all bit-exact (SURVEY.md 8a semantics 3)."""
+    from blitzen_b200 import scene
+    sc = small_scene
+    W, H = 640, 360
+    frame_views = [view_at(position=(380, 380, 380), z_far=2000.0, width=W, height=H)] * 2 + \
+                  [view_at(position=(380, 380, 380), yaw=0.5, z_far=2000.0, width=W, height=H)]   # the camera turns in frame 2
+    depth = scene.synthetic_depth(W, H, n_rects=40, z_min=20.0, z_max=400.0, seed=99)
+    rw = 6 if fmt == 0 else 8
+    n = len(sc["objs"])
+    vis = np.zeros(n, dtype=np.uint32)
+    with make_ctx(capi, sc) as ctx:
+        ctx.set_view(frame_views[0])
+        ctx.clear_pyramid(hiz, W, H)
+        pyr = O.cleared_pyramid(W, H, hiz)
+        for frame in range(3):
+            view = frame_views[frame]
+            ctx.set_view(view)
+            e_exp, e_tot, _ = O.cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_EARLY, rec_words=rw, vis=vis)
+            ctx.early(fmt)
+            e_got, e_gtot = ctx.read_draws(fmt)
+            assert e_gtot == e_tot and np.array_equal(recs_u32(e_got), e_exp), f"early frame {frame}"
+            if frame > 0:
+                ctx.set_depth(depth)
+                ctx.build_pyramid(hiz)
+                pyr = O.build_pyramid(depth, hiz)
+            l_exp, l_tot, vis = O.cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_LATE, rec_words=rw, hiz=hiz, pyramid=pyr, vis=vis)
+            ctx.late(fmt, hiz)
+            l_got, l_gtot = ctx.read_draws(fmt)
+            assert l_gtot == l_tot and np.array_equal(recs_u32(l_got), l_exp), f"late frame {frame}"
+            assert np.array_equal(ctx.read_visibility(), vis), f"visibility frame {frame}"
+            if frame == 0:
+                assert e_tot == 0 and l_tot > 0
+            if frame == 2:
+                assert e_tot > 0 and l_tot > 0      # newly visible objects are emitted by the late pass
+        assert 0 < int(vis.sum()) < n
+
+
+def test_capacity_clamp(capi, small_scene):
+    sc = small_scene
+    view = view_at(position=(380, 380, -2500), z_far=1e9)
+    cap = 12_345
+    exp, total, _ = O.cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM, capacity=cap)
+    with make_ctx(capi, sc, draw_capacity=cap) as ctx:
+        ctx.set_view(view)
+        ctx.frustum_lod()
+        written, gtotal = ctx.read_count()
+        got, _ = ctx.read_draws()
+    assert written == cap and gtotal == total == len(sc["objs"])
+    assert np.array_equal(recs_u32(got), exp)
+
+
+def test_instanced(capi, small_scene):
+    sc = small_scene
+    view = view_at(position=(380, 380, 380), z_far=2000.0)
+    li = sc["lodInstances"].copy()
+    nl = len(sc["lods"])
+    cap = np.full(nl, 4000, dtype=np.uint32)
+    cap[3] = 7
+    li["instanceOffset"] = np.concatenate([[0], np.cumsum(cap)[:-1]]).astype(np.uint32)
+    idx_e, cnt_e, cmds_e = O.cull_instanced(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], li, cap, view)
+    with make_ctx(capi, sc, lod_instances=li, bucket_capacity=cap) as ctx:
+        ctx.set_view(view)
+        for _ in range(2):
+            ctx.instanced()
+            cmds, total = ctx.read_draws(capi.REC_DX32)
+            idx, counters = ctx.read_instances(int(cap.sum()))
+            assert np.array_equal(counters["instanceCount"], cnt_e)
+            assert np.array_equal(recs_u32(cmds), cmds_e) and total == len(cmds_e)
+            for l in range(nl):
+                o, c = int(li["instanceOffset"][l]), int(min(cnt_e[l], cap[l]))
+                assert np.array_equal(idx[o:o + c], idx_e[o:o + c]), f"bucket {l}"
+    assert cnt_e[7] > cap[7]      # the overflowing bucket really overflowed
+
+
+def test_cluster_path(capi, small_scene):
+    sc = small_scene
+    view = view_at(position=(380, 380, 380), z_far=400.0)
+    capacity = 3_000_000
+    d_exp, d_tot = O.cluster_expand(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, capacity)
+    assert 0 < d_tot <= capacity
+    W, H = 640, 360
+    from blitzen_b200 import scene
+    depth = scene.synthetic_depth(W, H, n_rects=40, z_min=20.0, z_max=300.0, seed=5)
+    with make_ctx(capi, sc, cluster_dispatch_capacity=capacity, draw_capacity=capacity) as ctx:
+        ctx.set_view(view)
+        ctx.cluster_expand()
+        d_got, d_gtot = ctx.read_cluster_dispatch()
+        assert d_gtot == d_tot
+        assert np.array_equal(d_got.view(np.uint32).reshape(-1, 3), d_exp)
+        for fmt in (0, 1):
+            rw = 6 if fmt == 0 else 8
+            exp, tot = O.cluster_cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], sc["clusters"], view, d_exp, 0, rec_words=rw)
+            ctx.cluster_cull(capi.CLUSTER_PASSTHROUGH, fmt)
+            got, gtot = ctx.read_draws(fmt)
+            assert gtot == tot == d_tot and np.array_equal(recs_u32(got), exp)
+        exp, tot = O.cluster_cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], sc["clusters"], view, d_exp, 1)
+        ctx.cluster_cull(capi.CLUSTER_SPHERE, 0)
+        got, gtot = ctx.read_draws(0)
+        assert gtot == tot and 0 < tot < d_tot and np.array_equal(recs_u32(got), exp)
+        for hiz in (0, 1):
+            ctx.set_depth(depth); ctx.build_pyramid(hiz)
+            pyr = O.build_pyramid(depth, hiz)
+            exp, tot = O.cluster_cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], sc["clusters"], view, d_exp, 1, hiz=hiz, pyramid=pyr)
+            ctx.cluster_cull(capi.CLUSTER_SPHERE_HIZ, 0, hiz)
+            got, gtot = ctx.read_draws(0)
+            assert gtot == tot and np.array_equal(recs_u32(got), exp)
+
+
+def test_onpc_quirk_and_lists(capi, small_scene):
+    sc = small_scene
+    view = view_at(position=(380, 380, 380), z_far=2000.0)
+    onpc = sc["objs"][5000:5100].copy()
+    transp = sc["objs"][20000:29000].copy()
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], transparent=transp, onpc=onpc)
+        ctx.set_view(view)
+        exp, tot, _ = O.cull(onpc, sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM, flags=O.FLAG_ONPC_LOD_QUIRK)
+        ctx.frustum_lod(capi.LIST_ONPC, 0, capi.FLAG_ONPC_LOD_QUIRK)
+        got, gtot = ctx.read_draws()
+        assert gtot == tot and np.array_equal(recs_u32(got), exp)
+        exp, tot, _ = O.cull(transp, sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM)
+        ctx.frustum_lod(capi.LIST_TRANSPARENT, 0)
+        got, gtot = ctx.read_draws()
+        assert gtot == tot and np.array_equal(recs_u32(got), exp)
+
+
+def test_update_transforms(capi, small_scene):
+    sc = small_scene
+    view = view_at(position=(50, 50, -200), z_far=2000.0)
+    xf = sc["transforms"].copy()
+    rng = np.random.default_rng(3)
+    xf["pos"][:1000] += rng.standard_normal((1000, 3)).astype(np.float32) * 20
+    xf["orientation"][:1000] = rng.standard_normal((1000, 4)).astype(np.float32)   # non-unit quaternions on purpose
+    with make_ctx(capi, sc) as ctx:
+        ctx.set_view(view)
+        ctx.update_transforms(0, xf[:1000])
+        ctx.frustum_lod()
+        got, gtot = ctx.read_draws()
+    exp, tot, _ = O.cull(sc["objs"], xf, sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM)
+    assert gtot == tot and np.array_equal(recs_u32(got), exp)
+
+
+def test_empty_and_tiny(capi, tables):
+    from blitzen_b200 import scene
+    view = view_at(position=(0, 0, -50), z_far=1e6)
+    for n in (1, 31, 32, 33, 1023, 1024, 1025):
+        objs, xf = scene.generate(groups=((0, 5.0, n),), multiplier=30.0, prologue=False, prng="counter", seed=n)
+        transforms, base = scene.assemble_transforms(objs, xf, 0)
+        exp, tot, _ = O.cull(objs, transforms, tables["surfaces"], tables["lods"], view, O.PASS_FRUSTUM)
+        with capi.CullContext(0) as ctx:
+            ctx.upload_scene(objs, transforms, tables["surfaces"], tables["lods"])
+            ctx.set_view(view)
+            ctx.frustum_lod()
+            got, gtot = ctx.read_draws()
+        assert gtot == tot == n and np.array_equal(recs_u32(got), exp)
+
+
+def test_sharded_ids(capi, small_scene):
+    """object_id_base / transform_id_base: a shard produces the same records as the matching slice of the full list."""
+    sc = small_scene
+    view = view_at(position=(380, 380, 380), z_far=2000.0)
+    full, _, _ = O.cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM)
+    n = len(sc["objs"])
+    parts = []
+    for r in range(3):
+        a, b = (r * n) // 3, ((r + 1) * n) // 3
+        objs = sc["objs"][a:b]
+        lo, hi = int(objs["transformId"].min()), int(objs["transformId"].max()) + 1
+        with capi.CullContext(0) as ctx:
+            ctx.upload_scene(objs, sc["transforms"][lo:hi], sc["surfaces"], sc["lods"], object_id_base=a, transform_id_base=lo)
+            ctx.set_view(view)
+            ctx.frustum_lod()
+            got, _ = ctx.read_draws()
+        parts.append(recs_u32(got))
+    assert np.array_equal(np.concatenate(parts), full)
