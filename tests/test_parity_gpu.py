@@ -22,7 +22,7 @@ def make_ctx(capi, sc, **kw):
 
 
 def recs_u32(rec):
-    return rec.view(np.uint32).reshape(len(rec), -1)
+    return rec.view(np.uint32).reshape(len(rec), rec.dtype.itemsize // 4)
 
 
 SMALL_VIEWS = {
