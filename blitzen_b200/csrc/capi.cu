@@ -121,6 +121,21 @@ int ensure_pyramid_storage(blz_cull_ctx* c, int variant, uint32_t depthW, uint32
     return BLZ_OK;
 }
 
+// grows a device buffer only when it is too small, so that re-uploading a scene of the same shape (bench.py's end-to-end
+// leg, streaming scenes) costs copies and one repack launch, not cudaMalloc/cudaFree
+template <class T>
+int grow(blz_cull_ctx* c, T*& p, size_t& capBytes, size_t needBytes)
+{
+    if (needBytes == 0) needBytes = 16;
+    if (p && capBytes >= needBytes) return BLZ_OK;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (p) { cudaFree(p); p = nullptr; capBytes = 0; }
+    CU_TRY(cudaMalloc(&p, needBytes));
+    capBytes = needBytes;
+    return BLZ_OK;
+}
+#define TRY_RC(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
 int check_list(blz_cull_ctx* c, int list)
 {
     if (list < 0 || list > 2) return fail(BLZ_ERR_INVALID, "list %d out of range", list);
@@ -205,6 +220,9 @@ static void free_scene(blz_cull_ctx* c)
     dfree(c->surf); dfree(c->lods); dfree(c->clusters); dfree(c->lodInst); dfree(c->bucketCap);
     dfree(c->vis); dfree(c->draws); dfree(c->dispatch); dfree(c->instIdx);
     c->nSurf = c->nLods = c->nClusters = c->nLodInst = 0; c->drawCap = c->dispatchCap = c->instCap = 0;
+    c->capObjs[0] = c->capObjs[1] = c->capObjs[2] = 0;
+    c->capXfPS = c->capXfQ = c->capSurf = c->capLods = c->capClusters = c->capLodInst = c->capBucket = 0;
+    c->capVis = c->capDraws = c->capDispatch = c->capInstIdx = 0;
 }
 
 int blz_cull_destroy(blz_cull_ctx* c)
@@ -244,90 +262,93 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     if (!c || !d) return fail(BLZ_ERR_INVALID, "null argument");
     if (!d->surfaces || d->surface_count == 0 || !d->lods || d->lod_count == 0) return fail(BLZ_ERR_INVALID, "surfaces and lods are required");
     if (!d->transforms || d->transform_count == 0) return fail(BLZ_ERR_INVALID, "transforms are required");
+    if (d->lod_instances && d->lod_instance_count && d->lod_instance_count != d->lod_count)
+        return fail(BLZ_ERR_INVALID, "lod_instance_count (%u) must equal lod_count (%u)", d->lod_instance_count, d->lod_count);
+    if (d->lod_instances && d->lod_instance_count && d->inputs_on_device && !d->instance_bucket_capacity)
+        return fail(BLZ_ERR_INVALID, "device inputs need explicit instance_bucket_capacity");
     CU_TRY(cudaSetDevice(c->device));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    free_scene(c);
     const cudaMemcpyKind kind = d->inputs_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const void* lists[3] = { d->renders, d->transparent_renders, d->onpc_renders };
     const uint32_t counts[3] = { d->render_count, d->transparent_count, d->onpc_count };
     uint64_t maxList = 0;
     for (int i = 0; i < 3; ++i) {
-        c->nObjs[i] = counts[i];
+        if (counts[i] && !lists[i]) return fail(BLZ_ERR_INVALID, "render list %d has a count but no pointer", i);
         if (counts[i] > maxList) maxList = counts[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+        c->nObjs[i] = counts[i];
         if (counts[i] == 0) continue;
-        if (!lists[i]) return fail(BLZ_ERR_INVALID, "render list %d has a count but no pointer", i);
-        CU_TRY(cudaMalloc(&c->objs[i], size_t(counts[i]) * sizeof(RenderObject)));
+        TRY_RC(grow(c, c->objs[i], c->capObjs[i], size_t(counts[i]) * sizeof(RenderObject)));
         CU_TRY(cudaMemcpyAsync(c->objs[i], lists[i], size_t(counts[i]) * sizeof(RenderObject), kind, c->stream));
     }
-    // transforms: AoS staging -> SoA repack (one-time; the per-frame path only reads the SoA streams)
+    // transforms: AoS staging -> SoA repack (the per-frame path only reads the two SoA streams)
     c->nXf = d->transform_count;
-    CU_TRY(cudaMalloc(&c->xfPS, size_t(c->nXf) * sizeof(float4)));
-    CU_TRY(cudaMalloc(&c->xfQ, size_t(c->nXf) * sizeof(float4)));
+    TRY_RC(grow(c, c->xfPS, c->capXfPS, size_t(c->nXf) * sizeof(float4)));
+    TRY_RC(grow(c, c->xfQ, c->capXfQ, size_t(c->nXf) * sizeof(float4)));
     {
-        MeshTransform* stage = nullptr;
         const MeshTransform* src = reinterpret_cast<const MeshTransform*>(d->transforms);
         if (!d->inputs_on_device) {
-            CU_TRY(cudaMalloc(&stage, size_t(c->nXf) * sizeof(MeshTransform)));
-            CU_TRY(cudaMemcpyAsync(stage, d->transforms, size_t(c->nXf) * sizeof(MeshTransform), cudaMemcpyHostToDevice, c->stream));
-            src = stage;
+            size_t capB = size_t(c->xfStageCap) * sizeof(MeshTransform);
+            TRY_RC(grow(c, c->xfStage, capB, size_t(c->nXf) * sizeof(MeshTransform)));
+            c->xfStageCap = uint32_t(capB / sizeof(MeshTransform));
+            CU_TRY(cudaMemcpyAsync(c->xfStage, d->transforms, size_t(c->nXf) * sizeof(MeshTransform), cudaMemcpyHostToDevice, c->stream));
+            src = c->xfStage;
         }
-        cudaError_t e = launch_repack_transforms(src, c->xfPS, c->xfQ, 0, c->nXf, c->stream);
+        CU_TRY(launch_repack_transforms(src, c->xfPS, c->xfQ, 0, c->nXf, c->stream));
         c->launches++;
-        cudaError_t e2 = cudaStreamSynchronize(c->stream);
-        if (stage) cudaFree(stage);
-        if (e != cudaSuccess) return fail(BLZ_ERR_CUDA, "transform repack launch failed: %s", cudaGetErrorString(e));
-        if (e2 != cudaSuccess) return fail(BLZ_ERR_CUDA, "transform repack failed: %s", cudaGetErrorString(e2));
     }
     c->nSurf = d->surface_count; c->nLods = d->lod_count;
-    CU_TRY(cudaMalloc(&c->surf, size_t(c->nSurf) * sizeof(PrimitiveSurface)));
+    TRY_RC(grow(c, c->surf, c->capSurf, size_t(c->nSurf) * sizeof(PrimitiveSurface)));
     CU_TRY(cudaMemcpyAsync(c->surf, d->surfaces, size_t(c->nSurf) * sizeof(PrimitiveSurface), kind, c->stream));
-    CU_TRY(cudaMalloc(&c->lods, size_t(c->nLods) * sizeof(LodData)));
+    TRY_RC(grow(c, c->lods, c->capLods, size_t(c->nLods) * sizeof(LodData)));
     CU_TRY(cudaMemcpyAsync(c->lods, d->lods, size_t(c->nLods) * sizeof(LodData), kind, c->stream));
+    c->nClusters = 0;
     if (d->clusters && d->cluster_count) {
         c->nClusters = d->cluster_count;
-        CU_TRY(cudaMalloc(&c->clusters, size_t(c->nClusters) * sizeof(Cluster)));
+        TRY_RC(grow(c, c->clusters, c->capClusters, size_t(c->nClusters) * sizeof(Cluster)));
         CU_TRY(cudaMemcpyAsync(c->clusters, d->clusters, size_t(c->nClusters) * sizeof(Cluster), kind, c->stream));
     }
     c->objectIdBase = d->object_id_base; c->transformIdBase = d->transform_id_base;
     // visibility buffer, zero-filled (vulkanRendererSetup.cpp:349)
     const size_t nVis = c->nObjs[0] ? c->nObjs[0] : 1;
-    CU_TRY(cudaMalloc(&c->vis, nVis * sizeof(uint32_t)));
+    TRY_RC(grow(c, c->vis, c->capVis, nVis * sizeof(uint32_t)));
     CU_TRY(cudaMemsetAsync(c->vis, 0, nVis * sizeof(uint32_t), c->stream));
-    // draw buffer
+    // draw buffer (sized for the wider DX32 record), cluster dispatch buffer
     c->drawCap = d->draw_capacity ? d->draw_capacity : (maxList ? maxList : 1);
-    CU_TRY(cudaMalloc(&c->draws, size_t(c->drawCap) * 8u * sizeof(uint32_t)));
-    // cluster dispatch buffer
+    TRY_RC(grow(c, c->draws, c->capDraws, size_t(c->drawCap) * 8u * sizeof(uint32_t)));
     c->dispatchCap = d->cluster_dispatch_capacity;
-    if (c->dispatchCap) CU_TRY(cudaMalloc(&c->dispatch, size_t(c->dispatchCap) * 3u * sizeof(uint32_t)));
+    if (c->dispatchCap) TRY_RC(grow(c, c->dispatch, c->capDispatch, size_t(c->dispatchCap) * 3u * sizeof(uint32_t)));
     // instancing
+    c->nLodInst = 0;
     if (d->lod_instances && d->lod_instance_count) {
-        if (d->inputs_on_device && !d->instance_bucket_capacity) return fail(BLZ_ERR_INVALID, "device inputs need explicit instance_bucket_capacity");
-        if (d->lod_instance_count != d->lod_count) return fail(BLZ_ERR_INVALID, "lod_instance_count (%u) must equal lod_count (%u)", d->lod_instance_count, d->lod_count);
         c->nLodInst = d->lod_instance_count;
-        CU_TRY(cudaMalloc(&c->lodInst, size_t(c->nLodInst) * sizeof(LodInstanceCounter)));
+        TRY_RC(grow(c, c->lodInst, c->capLodInst, size_t(c->nLodInst) * sizeof(LodInstanceCounter)));
         CU_TRY(cudaMemcpyAsync(c->lodInst, d->lod_instances, size_t(c->nLodInst) * sizeof(LodInstanceCounter), kind, c->stream));
         std::vector<uint32_t> cap(c->nLodInst);
         std::vector<LodInstanceCounter> li(c->nLodInst);
-        if (d->inputs_on_device) CU_TRY(cudaMemcpy(li.data(), d->lod_instances, li.size() * sizeof(LodInstanceCounter), cudaMemcpyDeviceToHost));
-        else memcpy(li.data(), d->lod_instances, li.size() * sizeof(LodInstanceCounter));
-        uint64_t end = 0;
-        for (uint32_t l = 0; l < c->nLodInst; ++l) {
-            if (d->instance_bucket_capacity) {
-                if (d->inputs_on_device) { uint32_t v; CU_TRY(cudaMemcpy(&v, d->instance_bucket_capacity + l, 4, cudaMemcpyDeviceToHost)); cap[l] = v; }
-                else cap[l] = d->instance_bucket_capacity[l];
-            } else {
-                // reference: instanceOffset = lodId * Ce_MaxInstanceCountPerLOD (Resources/Mesh/blitzenMeshes.cpp:159-161, Core/blitzenEngine.h:65)
-                cap[l] = (l + 1 < c->nLodInst && li[l + 1].instanceOffset > li[l].instanceOffset) ? li[l + 1].instanceOffset - li[l].instanceOffset : 100000u;
+        if (d->inputs_on_device) {
+            CU_TRY(cudaMemcpy(li.data(), d->lod_instances, li.size() * sizeof(LodInstanceCounter), cudaMemcpyDeviceToHost));
+            CU_TRY(cudaMemcpy(cap.data(), d->instance_bucket_capacity, cap.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        } else {
+            memcpy(li.data(), d->lod_instances, li.size() * sizeof(LodInstanceCounter));
+            for (uint32_t l = 0; l < c->nLodInst; ++l) {
+                // default: the reference's fixed bucket, instanceOffset = lodId * Ce_MaxInstanceCountPerLOD
+                // (Resources/Mesh/blitzenMeshes.cpp:159-161, Core/blitzenEngine.h:65)
+                if (d->instance_bucket_capacity) cap[l] = d->instance_bucket_capacity[l];
+                else cap[l] = (l + 1 < c->nLodInst && li[l + 1].instanceOffset > li[l].instanceOffset) ? li[l + 1].instanceOffset - li[l].instanceOffset : 100000u;
             }
-            if (uint64_t(li[l].instanceOffset) + cap[l] > end) end = uint64_t(li[l].instanceOffset) + cap[l];
         }
+        uint64_t end = 0;
+        for (uint32_t l = 0; l < c->nLodInst; ++l)
+            if (uint64_t(li[l].instanceOffset) + cap[l] > end) end = uint64_t(li[l].instanceOffset) + cap[l];
         c->instCap = end ? end : 1;
-        CU_TRY(cudaMalloc(&c->bucketCap, size_t(c->nLodInst) * sizeof(uint32_t)));
+        TRY_RC(grow(c, c->bucketCap, c->capBucket, size_t(c->nLodInst) * sizeof(uint32_t)));
         CU_TRY(cudaMemcpyAsync(c->bucketCap, cap.data(), cap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        CU_TRY(cudaMalloc(&c->instIdx, size_t(c->instCap) * sizeof(uint32_t)));
-        CU_TRY(cudaStreamSynchronize(c->stream));   // cap vector leaves scope
+        TRY_RC(grow(c, c->instIdx, c->capInstIdx, size_t(c->instCap) * sizeof(uint32_t)));
+        CU_TRY(cudaStreamSynchronize(c->stream));   // `cap` leaves scope
     }
-    CU_TRY(cudaStreamSynchronize(c->stream));
+    // Asynchronous with respect to the host when the sources are pinned; pageable sources are staged by the runtime before
+    // cudaMemcpyAsync returns.  Either way the caller may reuse its arrays after blz_cull_synchronize().
     return BLZ_OK;
 }
 

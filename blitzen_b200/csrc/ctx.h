@@ -18,6 +18,9 @@ struct blz_cull_ctx {
     blz::LodInstanceCounter* lodInst = nullptr; uint32_t nLodInst = 0;
     uint32_t* bucketCap = nullptr;
     uint32_t objectIdBase = 0, transformIdBase = 0;
+    // allocation sizes in bytes (buffers only ever grow; see grow() in capi.cu)
+    size_t capObjs[3] = { 0, 0, 0 }, capXfPS = 0, capXfQ = 0, capSurf = 0, capLods = 0, capClusters = 0, capLodInst = 0, capBucket = 0;
+    size_t capVis = 0, capDraws = 0, capDispatch = 0, capInstIdx = 0;
     // per-object state + outputs
     uint32_t* vis = nullptr;
     uint32_t* draws = nullptr; uint64_t drawCap = 0;
