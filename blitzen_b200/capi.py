@@ -138,6 +138,10 @@ class CullContext:
         self.n_objects = 0
         self.n_lods = 0
         self._keep = []
+        # A/B knobs for measurements (bench.py / profiling scripts), e.g. BLZ_OPTIONS="cull_items=4,pyramid_tma=0"
+        for kv in filter(None, os.environ.get("BLZ_OPTIONS", "").split(",")):
+            k, v = kv.split("=")
+            self.set_option(k.strip(), int(v))
 
     def _check(self, rc):
         if rc != 0:

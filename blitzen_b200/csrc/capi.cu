@@ -159,8 +159,8 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.objs = c->objs[list]; p.n = c->nObjs[list];
     p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
     p.visibility = c->vis; p.draws = c->draws; p.counts = c->counts; p.ctl = c->ctl;
-    p.numTiles = tiles_for(p.n);
-    rc = ensure_status(c, p.numTiles); if (rc) return rc;
+    p.numTiles = tiles_for(p.n);                      // re-derived from `items` by the launcher
+    rc = ensure_status(c, p.n / kCullMinTile + 2u); if (rc) return rc;
     p.status = c->status;
     p.objectIdBase = list == BLZ_LIST_OPAQUE ? c->objectIdBase : 0u;
     p.transformIdBase = c->transformIdBase;

@@ -1,35 +1,54 @@
-// Draw-cull passes: frustum / early / late (Hi-Z) / temporal, one persistent kernel each, replacing
+// Draw-cull passes: frustum / early / late (Hi-Z) / temporal, one persistent software-pipelined kernel each, replacing
 //   VulkanShaders/{Initial,Late,Transparent,Onpc}DrawCull.comp.glsl and HlslShaders/CS/{drawCull,drawOccFirst,drawOccLate,drawOccTemporal}
 // (paths relative to /root/reference/src/Renderer).
 //
-// Mapping to the hardware (B200, 148 SMs, HBM-bound):
-//   * persistent grid = numSMs x resident CTAs; tiles of kCullTile consecutive objects are handed out by an atomic ticket,
-//     so tile order == object order and every predecessor of a tile is already running (look-back cannot deadlock).
-//   * a warp owns 32*ITEMS consecutive objects; lane l handles objects l, l+32, ... -> every global access of a warp is one
-//     contiguous, fully used span: RenderObject 8 B/lane (LDG.64), visibility 4 B/lane, transforms 2 x 16 B/lane (LDG.128)
-//     from the SoA repack.  All loads of a tile are issued before the first use (ITEMS*3 independent requests per thread).
-//   * the surface and LOD tables (a few KB) are copied to shared memory once per CTA.
-//   * survivors are ranked with ballot/popc inside the warp, by an 8-entry shared scan inside the CTA and by a decoupled
-//     look-back across tiles; records are staged in shared memory and leave the CTA as one contiguous, coalesced span.
-//   * view constants arrive as kernel parameters (constant bank operands), not loads.
+// Mapping to the hardware (B200, 148 SMs, HBM-bound).  History of the measurements that shaped it is in DESIGN.md; the
+// ncu captures are profiles/r01a_* (first version: 29 % of the HBM peak, 40-57 % of the stalls at CTA barriers and in the
+// look-back spin) and profiles/r01b_* (per-warp pending loops: 240 M warp instructions, 3 of 32 lanes active in Hi-Z).
+//
+//   * persistent grid = numSMs x 2 CTAs of 512 threads; tiles of 1024 consecutive objects are handed out by an atomic
+//     ticket claimed three tiles ahead, so tile order == claim order and every predecessor of a tile belongs to a running CTA.
+//   * every input stream is staged through shared memory by cp.async (LDGSTS), issued by the thread that later consumes it
+//     (no barrier on the input side): iteration j consumes tile j, then re-fills the slots it just read with the
+//     RenderObject / visibility words of tile j+2 and the two 16-B transform halves of tile j+1 (gather by transformId,
+//     which arrived one iteration earlier).  ~44 KB of loads per CTA are in flight whatever the CTA is doing.
+//   * lane l of a warp owns objects l and l+32 of the warp's 64-object span: every global access of a warp is one
+//     contiguous, fully used run of sectors (4 B, 8 B or 16 B per lane).
+//   * surface + LOD tables (KB) live in shared memory; view constants are kernel parameters (constant bank).
+//   * DENSE step (all objects): view-space sphere + frustum planes, ~70 FP32 instructions, nothing else.
+//     Survivors (a few %) are pushed into a CTA-wide queue in shared memory.
+//   * SPARSE step (queue entries, one per thread): projectSphere (2 sqrt + 5 IEEE div), Hi-Z fetch, LOD loop.  Runs with
+//     full warps instead of 3 active lanes out of 32.
+//   * compaction is deterministic and chain-free: ballot/popc inside the warp, a 16-entry scan inside the CTA, and across
+//     tiles every CTA sums the published per-tile AGGREGATES between its previous tile and the current one (coalesced
+//     reads of 8-B epoch-tagged words, L2 hits).  No tile ever waits for another tile's prefix, only for aggregates, and
+//     the sum is taken two tiles late, so the wait is not exposed.
+//   * survivors are staged as 4-B descriptors {index in tile, lodId}; the 24-/32-B records are expanded on the way out
+//     and leave the CTA as one contiguous, coalesced span of 8-B stores.
 #include "cull_kernels.cuh"
 #include "cull_math.cuh"
 #include "scan_lookback.cuh"
 
 namespace blz {
 
-__device__ __forceinline__ uint2 ldg_nc_u2(const void* p)
+namespace {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async4(void* dst, const void* src)
 {
-    uint2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-    return v;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ float4 ldg_nc_f4(const void* p)
+__device__ __forceinline__ void cp_async8(void* dst, const void* src)
 {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p)
 {
     uint32_t v;
@@ -39,165 +58,287 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p)
 __device__ __forceinline__ void st_cs_u32(uint32_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_cs_u2(void* p, uint2 v) { asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory"); }
 
-// Surface / LOD table access, either from the shared-memory copy or straight from global (tables too large for smem).
-struct Tables {
-    const PrimitiveSurface* surf;
-    const LodData* lod;
-};
+constexpr int kTileRing = 8;             // ring of claimed tile ids (power of two, > prefetch distance + 2)
+constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+constexpr int kLag = 2;                  // the prefix of a tile is resolved (and its records written) this many tiles later
+constexpr int kStages = kLag + 1;        // descriptor buffers
+constexpr uint32_t kLocalBits = 10;      // kDrawTile == 1 << kLocalBits
+static_assert(kDrawTile == (1 << kLocalBits), "descriptor packing");
 
-template <int PASS, int HIZ, bool SMEM_TABLES, int ITEMS>
-__global__ void __launch_bounds__(kCullThreads, 4) draw_cull_kernel(const __grid_constant__ DrawCullParams p)
+} // namespace
+
+template <int PASS, int HIZ, bool SMEM_TABLES>
+__global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid_constant__ DrawCullParams p)
 {
-    constexpr int TILE = kCullThreads * ITEMS;
-    constexpr int WARPS = kCullThreads / 32;
+    constexpr int ITEMS = kDrawItems, TILE = kDrawTile, THREADS = kDrawThreads, WARPS = THREADS / 32;
+    constexpr bool HAS_VIS = (PASS == PASS_EARLY || PASS == PASS_LATE);
+    constexpr bool HAS_HIZ = (PASS == PASS_LATE || PASS == PASS_TEMPORAL);
+    constexpr int DV = (PASS == PASS_EARLY) ? 3 : 2;     // prefetch distance of the visibility words (the early pass needs them to ask for objects)
+    constexpr int NV = DV;                                // ring depth: the slot of tile j is re-filled with tile j+DV right after it is read
+
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_tiles[kTileRing];
     __shared__ uint32_t s_warpCnt[WARPS];
-    __shared__ uint32_t s_tile, s_prefix;
+    __shared__ uint32_t s_red[WARPS];
+    __shared__ uint32_t s_qCount;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t laneLt = (1u << lane) - 1u;
 
-    Tables T;
-    uint32_t* staging;
+    // ---- carve shared memory --------------------------------------------------------------------------------------------
+    unsigned char* sp = smem_raw;
+    const PrimitiveSurface* surfT = p.surfaces;
+    const LodData* lodT = p.lods;
     if (SMEM_TABLES) {
-        uint4* dstS = reinterpret_cast<uint4*>(smem_raw);
+        uint4* dstS = reinterpret_cast<uint4*>(sp);
         const uint4* srcS = reinterpret_cast<const uint4*>(p.surfaces);
-        for (uint32_t i = tid; i < p.surfaceCount * 2u; i += kCullThreads) dstS[i] = __ldg(srcS + i);
+        for (uint32_t i = tid; i < p.surfaceCount * 2u; i += THREADS) dstS[i] = __ldg(srcS + i);
         uint4* dstL = dstS + p.surfaceCount * 2u;
         const uint4* srcL = reinterpret_cast<const uint4*>(p.lods);
-        for (uint32_t i = tid; i < p.lodCount * 2u; i += kCullThreads) dstL[i] = __ldg(srcL + i);
-        T.surf = reinterpret_cast<const PrimitiveSurface*>(dstS);
-        T.lod = reinterpret_cast<const LodData*>(dstL);
-        staging = reinterpret_cast<uint32_t*>(dstL + p.lodCount * 2u);
-    } else {
-        T.surf = p.surfaces;
-        T.lod = p.lods;
-        staging = reinterpret_cast<uint32_t*>(smem_raw);
+        for (uint32_t i = tid; i < p.lodCount * 2u; i += THREADS) dstL[i] = __ldg(srcL + i);
+        surfT = reinterpret_cast<const PrimitiveSurface*>(dstS);
+        lodT = reinterpret_cast<const LodData*>(dstL);
+        sp = reinterpret_cast<unsigned char*>(dstL + p.lodCount * 2u);
     }
-    const uint32_t epoch = ld_cg_u32(&p.ctl->epoch);   // constant for the whole launch (only the last CTA to leave bumps it)
+    float4* xfPS = reinterpret_cast<float4*>(sp);          sp += size_t(TILE) * sizeof(float4);        // transforms of the tile about to be consumed
+    float4* xfQ = reinterpret_cast<float4*>(sp);           sp += size_t(TILE) * sizeof(float4);
+    float4* qSphere = reinterpret_cast<float4*>(sp);       sp += size_t(TILE) * sizeof(float4);        // survivor queue
+    uint2* qMeta = reinterpret_cast<uint2*>(sp);           sp += size_t(TILE) * sizeof(uint2);         //   {scale bits, index in tile | visPrev << 16}
+    uint2* objRing = reinterpret_cast<uint2*>(sp);         sp += size_t(2) * TILE * sizeof(uint2);
+    uint32_t* qSurf = reinterpret_cast<uint32_t*>(sp);     sp += size_t(TILE) * sizeof(uint32_t);      //   surfaceId
+    uint32_t* sRes = reinterpret_cast<uint32_t*>(sp);      sp += size_t(TILE) * sizeof(uint32_t);      // visible | emit << 1 | lodId << 2, per object of the tile
+    uint32_t* stage = reinterpret_cast<uint32_t*>(sp);     sp += size_t(kStages) * TILE * sizeof(uint32_t);
+    uint32_t* visRing = reinterpret_cast<uint32_t*>(sp);   // NV * TILE words (only when HAS_VIS)
+
+    const uint32_t epoch = ld_cg_u32(&p.ctl->epoch) & 0x3FFFFFFFu;   // constant for the whole launch (the last CTA out bumps it)
     const ViewConsts& V = p.view;
+    const uint32_t localBase = warp * uint32_t(32 * ITEMS) + lane;    // + k*32 = index inside the tile
+    const uint32_t nLast = p.n ? p.n - 1u : 0u;
 
-    while (true) {
-        if (tid == 0) s_tile = atomicAdd(&p.ctl->ticket, 1u);
-        __syncthreads();   // (A) ticket visible; previous tile's staging fully drained; tables loaded
-        const uint32_t tile = s_tile;
-        if (tile >= p.numTiles) break;
-        const uint32_t base = tile * uint32_t(TILE) + warp * uint32_t(32 * ITEMS) + lane;
+    if (tid == 0) { s_tiles[0] = atomicAdd(&p.ctl->ticket, 1u); s_qCount = 0u; }
+    __syncthreads();     // first tile + tables visible
 
-        // ---- phase 1: issue every load of the tile -------------------------------------------------------------
-        bool act[ITEMS];
-        uint2 obj[ITEMS];
-        uint32_t visPrev[ITEMS];
+    uint64_t cum = 0;                  // records emitted by tiles [0, nextRead)
+    uint32_t nextRead = 0;             // first tile whose aggregate this CTA has not summed yet
+    uint32_t histTile[kLag], histTotal[kLag];
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const uint32_t i = base + uint32_t(k) * 32u;
-            act[k] = i < p.n;
-            visPrev[k] = 0u;
-            if (PASS == PASS_EARLY || PASS == PASS_LATE) {
-                if (act[k]) visPrev[k] = ld_cg_u32(p.visibility + i);
-                if (PASS == PASS_EARLY) act[k] = act[k] && (visPrev[k] != 0u);    // InitialDrawCull.comp.glsl:21-24
+    for (int h = 0; h < kLag; ++h) { histTile[h] = kNoTile; histTotal[h] = 0u; }
+
+    for (int j = -DV;; ++j) {
+        const uint32_t ju = uint32_t(j + 2 * kTileRing * kStages * NV);   // j shifted to a non-negative value with the same residues
+        const uint32_t tile = j >= 0 ? s_tiles[ju & (kTileRing - 1)] : kNoTile;
+        const bool valid = tile < p.numTiles;          // uniform over the CTA
+        // thread 0 claims the ticket of sequence slot j+DV+1 now and publishes it after barrier S2 (latency hidden); it is read
+        // for the first time in iteration j+1.  Once a claimed tile is past the end every later one is too.
+        uint32_t ticket = kNoTile;
+        if (tid == 0 && s_tiles[(ju + uint32_t(DV)) & (kTileRing - 1)] < p.numTiles) ticket = atomicAdd(&p.ctl->ticket, 1u);
+
+        // ---- step 1, dense: sphere + frustum for the ITEMS objects of this thread; survivors go to the CTA queue ----------
+        cp_async_wait_all();               // everything this thread asked for one and two iterations ago has landed
+        uint32_t survMask = 0u;
+        if (valid) {
+            const uint32_t tileBase = tile * uint32_t(TILE);
+            uint32_t visPrevMask = 0u;
+            Sphere sph[ITEMS]; float scl[ITEMS]; uint32_t sid[ITEMS];
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const uint32_t l = localBase + uint32_t(k) * 32u, i = tileBase + l;
+                bool act = i < p.n;
+                if (HAS_VIS) {
+                    const uint32_t vp = visRing[(ju % uint32_t(NV)) * TILE + l];
+                    if (act && vp != 0u) visPrevMask |= 1u << k;
+                    if (PASS == PASS_EARLY) act = act && (vp != 0u);                     // InitialDrawCull.comp.glsl:21-24
+                }
+                sph[k] = Sphere{ 0.f, 0.f, 0.f, 0.f }; scl[k] = 1.f; sid[k] = 0u;
+                if (act) {
+                    const uint2 ob = objRing[(ju & 1u) * TILE + l];
+                    const float4 ps = xfPS[l], qt = xfQ[l];
+                    const float4 bs = *reinterpret_cast<const float4*>(&surfT[ob.y]);   // {center.xyz, radius}
+                    sid[k] = ob.y; scl[k] = ps.w;
+                    sph[k] = view_space_sphere(bs.x, bs.y, bs.z, bs.w, ps.x, ps.y, ps.z, ps.w, qt.x, qt.y, qt.z, qt.w, V);
+                    if (frustum_test(sph[k], V)) survMask |= 1u << k;
+                }
             }
-            obj[k] = make_uint2(0u, 0u);
-            if (act[k]) obj[k] = ldg_nc_u2(p.objs + i);
-        }
-        float4 ps[ITEMS], qt[ITEMS];
+            // queue push: one shared-memory atomic per warp
+            uint32_t ball[ITEMS], cnt = 0u;
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            ps[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            qt[k] = make_float4(0.f, 0.f, 0.f, 1.f);
-            if (act[k]) {
-                const uint32_t t = obj[k].x - p.transformIdBase;
-                ps[k] = ldg_nc_f4(p.xfPosScale + t);
-                qt[k] = ldg_nc_f4(p.xfQuat + t);
+            for (int k = 0; k < ITEMS; ++k) { ball[k] = __ballot_sync(0xFFFFFFFFu, (survMask >> k) & 1u); cnt += uint32_t(__popc(ball[k])); }
+            if (cnt != 0u) {
+                uint32_t base = 0u;
+                if (lane == 0) base = atomicAdd(&s_qCount, cnt);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k) {
+                    if ((survMask >> k) & 1u) {
+                        const uint32_t slot = base + uint32_t(__popc(ball[k] & laneLt));
+                        qSphere[slot] = make_float4(sph[k].x, sph[k].y, sph[k].z, sph[k].r);
+                        qMeta[slot] = make_uint2(__float_as_uint(scl[k]), (localBase + uint32_t(k) * 32u) | (((visPrevMask >> k) & 1u) << 16));
+                        qSurf[slot] = sid[k];
+                    }
+                    base += uint32_t(__popc(ball[k]));
+                }
             }
         }
-
-        // ---- phase 2: cull, LOD select, rank inside the warp ----------------------------------------------------
-        uint32_t emitMask = 0u;            // bit k: object k of this lane emits a record
-        uint32_t rank[ITEMS];
-        uint32_t lodAbs[ITEMS];
-        uint32_t running = 0u;
+        // ---- re-fill the slots just read: transforms of tile j+1, RenderObject / visibility of tile j+2 (j+DV) -------------
+        {
+            const uint32_t tN = j + 1 >= 0 ? s_tiles[(ju + 1u) & (kTileRing - 1)] : kNoTile;
+            if (tN < p.numTiles) {
 #pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            bool visible = false;
-            Sphere s{ 0.f, 0.f, 0.f, 0.f };
-            uint32_t lodOffset = 0u, lodCount = 0u;
-            if (act[k]) {
-                const PrimitiveSurface& sf = T.surf[obj[k].y];
-                lodOffset = sf.lodOffset; lodCount = sf.lodCount;
-                s = view_space_sphere(sf.center[0], sf.center[1], sf.center[2], sf.radius,
-                                      ps[k].x, ps[k].y, ps[k].z, ps[k].w, qt[k].x, qt[k].y, qt[k].z, qt[k].w, V);
-                visible = frustum_test(s, V);
-                if ((PASS == PASS_LATE || PASS == PASS_TEMPORAL) && visible) {
+                for (int k = 0; k < ITEMS; ++k) {
+                    const uint32_t l = localBase + uint32_t(k) * 32u;
+                    if (PASS == PASS_EARLY && visRing[((ju + 1u) % uint32_t(NV)) * TILE + l] == 0u) continue;
+                    if (PASS == PASS_EARLY && tN * uint32_t(TILE) + l >= p.n) continue;   // the clamped visibility word belongs to another object
+                    const uint32_t t = objRing[((ju + 1u) & 1u) * TILE + l].x - p.transformIdBase;
+                    cp_async16(xfPS + l, p.xfPosScale + t);
+                    cp_async16(xfQ + l, p.xfQuat + t);
+                }
+            }
+            const uint32_t tO = j + 2 >= 0 ? s_tiles[(ju + 2u) & (kTileRing - 1)] : kNoTile;
+            if (tO < p.numTiles) {
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k) {
+                    const uint32_t l = localBase + uint32_t(k) * 32u;
+                    const uint32_t i = min(tO * uint32_t(TILE) + l, nLast);
+                    if (PASS == PASS_EARLY && (visRing[((ju + 2u) % uint32_t(NV)) * TILE + l] == 0u || tO * uint32_t(TILE) + l >= p.n)) continue;
+                    cp_async8(objRing + (ju & 1u) * TILE + l, p.objs + i);
+                }
+            }
+            if (HAS_VIS) {
+                const uint32_t tV = s_tiles[(ju + uint32_t(DV)) & (kTileRing - 1)];
+                if (tV < p.numTiles) {
+#pragma unroll
+                    for (int k = 0; k < ITEMS; ++k) {
+                        const uint32_t l = localBase + uint32_t(k) * 32u;
+                        cp_async4(visRing + (ju % uint32_t(NV)) * TILE + l, p.visibility + min(tV * uint32_t(TILE) + l, nLast));
+                    }
+                }
+            }
+            cp_async_commit();
+        }
+        __syncthreads();   // (S1) queue complete
+
+        // ---- step 2, sparse: Hi-Z + LOD for the queue entries, one per thread ----------------------------------------------
+        if (valid) {
+            const uint32_t qn = s_qCount;
+            for (uint32_t e = tid; e < qn; e += THREADS) {
+                const float4 q = qSphere[e];
+                const uint2 m = qMeta[e];
+                const Sphere s{ q.x, q.y, q.z, q.w };
+                bool visible = true;
+                if (HAS_HIZ) {
                     float4 aabb;
                     if (project_sphere(s, V.zNear, V.proj0, V.proj5, aabb))
                         visible = (HIZ == HIZ_VK) ? hiz_test_vk(aabb, p.pyr, s, V) : hiz_test_dx(aabb, p.pyr, s, V);
                 }
+                bool emit = visible;
+                if (PASS == PASS_LATE) emit = visible && ((m.y >> 16) == 0u);                  // LateDrawCull.comp.glsl:49
+                uint32_t lodId = 0u;
+                if (emit) {
+                    const uint32_t sidx = qSurf[e];
+                    const uint32_t lodOffset = surfT[sidx].lodOffset, lodCount = surfT[sidx].lodCount;
+                    const uint32_t rel = lod_select(s, __uint_as_float(m.x), V.lodTarget, lodOffset, lodCount, [&](uint32_t li) { return lodT[li].error; });
+                    lodId = (p.flags & kFlagOnpcLodQuirk) ? rel : rel + lodOffset;
+                }
+                sRes[m.y & 0xFFFFu] = (visible ? 1u : 0u) | (emit ? 2u : 0u) | (lodId << 2);
             }
-            bool emit = visible;
-            if (PASS == PASS_LATE) {
-                emit = visible && (visPrev[k] == 0u);                            // LateDrawCull.comp.glsl:49
-                const uint32_t i = base + uint32_t(k) * 32u;
-                if (i < p.n) st_cs_u32(p.visibility + i, visible ? 1u : 0u);      // LateDrawCull.comp.glsl:70
-            }
-            lodAbs[k] = 0u;
-            if (emit) {
-                const uint32_t rel = lod_select(s, ps[k].w, V.lodTarget, lodOffset, lodCount,
-                                                [&](uint32_t li) { return T.lod[li].error; });
-                lodAbs[k] = (p.flags & kFlagOnpcLodQuirk) ? rel : rel + lodOffset;
-            }
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, emit);
-            rank[k] = running + uint32_t(__popc(ballot & laneLt));
-            running += uint32_t(__popc(ballot));
-            emitMask |= (emit ? 1u : 0u) << k;
         }
-        if (lane == 0) s_warpCnt[warp] = running;
-        __syncthreads();   // (B) warp counts visible
+        __syncthreads();   // (S2) results visible; nobody reads the queue counter any more
 
-        uint32_t warpOff = 0u, tileTotal = 0u;
+        // ---- step 3: read the results back, write visibility, rank the emitters, sum the aggregates for the lagging tile ----
+        if (tid == 0) { s_qCount = 0u; s_tiles[(ju + uint32_t(DV) + 1u) & (kTileRing - 1)] = ticket; }
+        uint32_t emitMask = 0u, rank[ITEMS], lodSel[ITEMS], running = 0u;
+        if (valid) {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const uint32_t c = s_warpCnt[w];
-            if (uint32_t(w) < warp) warpOff += c;
-            tileTotal += c;
+            for (int k = 0; k < ITEMS; ++k) {
+                const uint32_t l = localBase + uint32_t(k) * 32u, i = tile * uint32_t(TILE) + l;
+                const uint32_t r = ((survMask >> k) & 1u) ? sRes[l] : 0u;
+                if (PASS == PASS_LATE && i < p.n) st_cs_u32(p.visibility + i, r & 1u);          // LateDrawCull.comp.glsl:70
+                lodSel[k] = r >> 2;
+                const bool emit = (r & 2u) != 0u;
+                emitMask |= (emit ? 1u : 0u) << k;
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, emit);
+                rank[k] = running + uint32_t(__popc(ballot & laneLt));
+                running += uint32_t(__popc(ballot));
+            }
+            if (lane == 0) s_warpCnt[warp] = running;
         }
-        if (warp == 0) {
-            const uint32_t prefix = lookback_exclusive_prefix(p.status, tile, tileTotal, epoch, lane);
-            if (lane == 0) {
-                s_prefix = prefix;
-                if (tile == p.numTiles - 1u) {                                     // the draw count the indirect draw reads
-                    const uint64_t total = uint64_t(prefix) + tileTotal;
-                    p.counts[0] = uint32_t(total < p.capacity ? total : p.capacity);
-                    p.counts[1] = uint32_t(total);
+        const uint32_t outTile = histTile[kLag - 1], outTotal = histTotal[kLag - 1];
+        if (outTile != kNoTile) {
+            uint32_t part = 0u;
+            for (uint32_t t = nextRead + tid; t < outTile; t += THREADS) {
+                uint64_t w;
+                do { w = ld_status(p.status + t); } while (uint32_t(w >> 34) != epoch || (uint32_t(w >> 32) & 3u) == 0u);
+                part += uint32_t(w);
+            }
+            part = __reduce_add_sync(0xFFFFFFFFu, part);
+            if (lane == 0) s_red[warp] = part;
+        }
+        __syncthreads();   // (S3) warp counts + partial sums visible; descriptor buffer of tile j-kStages is free
+
+        // ---- step 4: stage this tile's descriptors + publish its aggregate; write out the records of tile j-kLag -------------
+        uint32_t tileTotal = 0u;
+        if (valid) {
+            uint32_t warpOff = 0u;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = s_warpCnt[w];
+                if (uint32_t(w) < warp) warpOff += c;
+                tileTotal += c;
+            }
+            if (tid == 0) st_status(p.status + tile, pack_status(epoch, kStateAggregate, tileTotal));
+            uint32_t* st = stage + (ju % uint32_t(kStages)) * TILE;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k)
+                if ((emitMask >> k) & 1u) st[warpOff + rank[k]] = (localBase + uint32_t(k) * 32u) | (lodSel[k] << kLocalBits);
+        }
+        if (outTile != kNoTile) {
+            uint64_t sum = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) sum += s_red[w];
+            const uint64_t prefix = cum + sum;                                                  // records before outTile
+            const uint64_t room = prefix < p.capacity ? p.capacity - prefix : 0ull;
+            const uint32_t nrec = uint32_t(room < outTotal ? room : outTotal);
+            const uint32_t* st = stage + ((ju + uint32_t(kStages - kLag)) % uint32_t(kStages)) * TILE;   // slot of iteration j - kLag
+            uint2* dst = reinterpret_cast<uint2*>(p.draws + prefix * p.recWords);
+            const uint32_t idBase = p.objectIdBase + outTile * uint32_t(TILE);
+            // {objectId, indexCount} {instanceCount = 1, firstIndex} {vertexOffset = 0, firstInstance = 0} [{pad, pad}]
+            if (p.recWords == 6u) {
+                for (uint32_t w = tid; w < nrec * 3u; w += THREADS) {
+                    const uint32_t r = w / 3u, f = w - r * 3u;
+                    const uint32_t d = st[r];
+                    const uint2 L = *reinterpret_cast<const uint2*>(&lodT[d >> kLocalBits]);    // {indexCount, firstIndex}
+                    st_cs_u2(dst + w, f == 0u ? make_uint2(idBase + (d & (TILE - 1u)), L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
+                }
+            } else {
+                for (uint32_t w = tid; w < nrec * 4u; w += THREADS) {
+                    const uint32_t r = w >> 2, f = w & 3u;
+                    const uint32_t d = st[r];
+                    const uint2 L = *reinterpret_cast<const uint2*>(&lodT[d >> kLocalBits]);
+                    st_cs_u2(dst + w, f == 0u ? make_uint2(idBase + (d & (TILE - 1u)), L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
                 }
             }
-        }
-        // ---- phase 3: stage the records of this warp in shared memory ---------------------------------------------
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            if (emitMask & (1u << k)) {
-                const LodData& lod = T.lod[lodAbs[k]];
-                uint32_t* r = staging + size_t(warpOff + rank[k]) * p.recWords;
-                const uint32_t i = base + uint32_t(k) * 32u;
-                // {objectId, indexCount, instanceCount = 1, firstIndex, vertexOffset = 0, firstInstance = 0 [, pad, pad]}
-                *reinterpret_cast<uint2*>(r + 0) = make_uint2(p.objectIdBase + i, lod.indexCount);
-                *reinterpret_cast<uint2*>(r + 2) = make_uint2(1u, lod.firstIndex);
-                *reinterpret_cast<uint2*>(r + 4) = make_uint2(0u, 0u);
-                if (p.recWords == 8u) *reinterpret_cast<uint2*>(r + 6) = make_uint2(0u, 0u);
+            if (outTile == p.numTiles - 1u && tid == 0) {                                      // the draw count the indirect draw reads
+                const uint64_t total = prefix + outTotal;
+                p.counts[0] = uint32_t(total < p.capacity ? total : p.capacity);
+                p.counts[1] = uint32_t(total);
             }
+            cum = prefix + outTotal;
+            nextRead = outTile + 1u;
         }
-        __syncthreads();   // (C) staging complete, prefix known
-
-        // ---- phase 4: one contiguous span per tile ---------------------------------------------------------------
-        const uint64_t prefix = s_prefix;
-        uint64_t room = prefix < p.capacity ? p.capacity - prefix : 0ull;
-        const uint32_t nrec = uint32_t(room < tileTotal ? room : tileTotal);
-        const uint32_t nwords64 = nrec * (p.recWords >> 1);
-        uint2* dst = reinterpret_cast<uint2*>(p.draws + prefix * p.recWords);
-        const uint2* src = reinterpret_cast<const uint2*>(staging);
-        for (uint32_t j = tid; j < nwords64; j += kCullThreads) st_cs_u2(dst + j, src[j]);
+        // shift the history of staged tiles
+#pragma unroll
+        for (int h = kLag - 1; h > 0; --h) { histTile[h] = histTile[h - 1]; histTotal[h] = histTotal[h - 1]; }
+        histTile[0] = valid ? tile : kNoTile; histTotal[0] = tileTotal;
+        if (j >= 0 && !valid) {
+            bool pending = false;
+#pragma unroll
+            for (int h = 0; h < kLag; ++h) pending = pending || (histTile[h] != kNoTile);
+            if (!pending) break;
+        }
     }
 
+    cp_async_wait_all();
+    if (p.n == 0u && blockIdx.x == 0 && tid == 0) { p.counts[0] = 0u; p.counts[1] = 0u; }
     // last CTA out re-arms the control block for the next launch on this stream
     if (tid == 0) {
         __threadfence();
@@ -211,24 +352,41 @@ __global__ void __launch_bounds__(kCullThreads, 4) draw_cull_kernel(const __grid
     }
 }
 
+static size_t draw_smem_bytes(int pass, bool smemTables, const DrawCullParams& p)
+{
+    const size_t tile = size_t(kDrawTile);
+    const bool hasVis = pass == PASS_EARLY || pass == PASS_LATE;
+    const size_t nv = pass == PASS_EARLY ? 3 : 2;
+    size_t b = smemTables ? (size_t(p.surfaceCount) + p.lodCount) * 32u : 0u;
+    b += tile * 16 * 2;                // transforms (two float4 streams, single buffer)
+    b += tile * (16 + 8 + 4);          // survivor queue: sphere, meta, surfaceId
+    b += 2 * tile * 8;                 // RenderObject ring
+    b += tile * 4;                     // per-object results of the sparse step
+    b += size_t(kStages) * tile * 4;   // survivor descriptors
+    if (hasVis) b += nv * tile * 4;
+    return b;
+}
+
 template <int PASS, int HIZ>
 static cudaError_t launch_variant(const DrawCullParams& p, int numSMs, cudaStream_t stream)
 {
+    if (p.lodCount >= (1u << (32 - kLocalBits))) return cudaErrorInvalidValue;     // descriptor packing (checked by the C-ABI layer too)
     const size_t tableBytes = (size_t(p.surfaceCount) + p.lodCount) * 32u;
-    const bool smemTables = tableBytes <= 16384u;
-    const size_t stagingBytes = size_t(kCullTile) * p.recWords * 4u;
-    const size_t smem = stagingBytes + (smemTables ? tableBytes : 0u);
-    auto kernel = smemTables ? draw_cull_kernel<PASS, HIZ, true, kCullItems> : draw_cull_kernel<PASS, HIZ, false, kCullItems>;
+    const bool smemTables = tableBytes <= 8192u;
+    const size_t smem = draw_smem_bytes(PASS, smemTables, p);
+    auto kernel = smemTables ? draw_cull_kernel<PASS, HIZ, true> : draw_cull_kernel<PASS, HIZ, false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     int perSM = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kCullThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kDrawThreads, smem);
     if (e != cudaSuccess) return e;
     if (perSM < 1) perSM = 1;
+    DrawCullParams q = p;
+    q.numTiles = uint32_t((uint64_t(p.n) + uint64_t(kDrawTile) - 1) / uint64_t(kDrawTile));
     uint32_t grid = uint32_t(numSMs) * uint32_t(perSM);
-    if (grid > p.numTiles) grid = p.numTiles;
+    if (grid > q.numTiles) grid = q.numTiles;
     if (grid < 1) grid = 1;
-    kernel<<<grid, kCullThreads, smem, stream>>>(p);
+    kernel<<<grid, kDrawThreads, smem, stream>>>(q);
     return cudaGetLastError();
 }
 

@@ -6,7 +6,11 @@ namespace blz {
 
 constexpr int kCullThreads = 256;                    // 8 warps per CTA
 constexpr int kCullItems = 4;                        // objects per thread
-constexpr int kCullTile = kCullThreads * kCullItems; // objects per tile (one ticket)
+constexpr int kCullTile = kCullThreads * kCullItems; // objects per tile (one ticket) of the instancing / cluster kernels
+constexpr int kDrawThreads = 512;                    // draw-cull kernels: 16 warps per CTA, 2 CTAs per SM
+constexpr int kDrawItems = 2;
+constexpr int kDrawTile = kDrawThreads * kDrawItems;
+constexpr int kCullMinTile = 1024;                   // smallest tile any kernel uses: sizes the per-tile status array
 
 struct DrawCullParams {
     // inputs
