@@ -62,13 +62,13 @@ constexpr int kTileRing = 8;             // ring of claimed tile ids (power of t
 constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 constexpr int kLag = 2;                  // the prefix of a tile is resolved (and its records written) this many tiles later
 constexpr int kStages = kLag + 1;        // descriptor buffers
-constexpr uint32_t kLocalBits = 10;      // kDrawTile == 1 << kLocalBits
+constexpr uint32_t kLocalBits = kDrawTile == 1024 ? 10 : 9;
 static_assert(kDrawTile == (1 << kLocalBits), "descriptor packing");
 
 } // namespace
 
 template <int PASS, int HIZ, bool SMEM_TABLES>
-__global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid_constant__ DrawCullParams p)
+__global__ void __launch_bounds__(kDrawThreads, kDrawThreads == 512 ? 2 : 4) draw_cull_kernel(const __grid_constant__ DrawCullParams p)
 {
     constexpr int ITEMS = kDrawItems, TILE = kDrawTile, THREADS = kDrawThreads, WARPS = THREADS / 32;
     constexpr bool HAS_VIS = (PASS == PASS_EARLY || PASS == PASS_LATE);
@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_tiles[kTileRing];
     __shared__ uint32_t s_warpCnt[WARPS];
-    __shared__ uint32_t s_red[WARPS];
+    __shared__ uint32_t s_totals[4];       // emit count of the tile of iteration j, at [j & 3]
+    __shared__ uint32_t s_sum[2];          // sum of the aggregates between this CTA's consecutive tiles (step 3 -> step 4), at [j & 1]
     __shared__ uint32_t s_qCount;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -115,14 +116,15 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
     const uint32_t localBase = warp * uint32_t(32 * ITEMS) + lane;    // + k*32 = index inside the tile
     const uint32_t nLast = p.n ? p.n - 1u : 0u;
 
-    if (tid == 0) { s_tiles[0] = atomicAdd(&p.ctl->ticket, 1u); s_qCount = 0u; }
+    if (tid == 0) { s_tiles[0] = atomicAdd(&p.ctl->ticket, 1u); s_qCount = 0u; s_sum[0] = 0u; s_sum[1] = 0u; }
     __syncthreads();     // first tile + tables visible
 
     uint64_t cum = 0;                  // records emitted by tiles [0, nextRead)
     uint32_t nextRead = 0;             // first tile whose aggregate this CTA has not summed yet
-    uint32_t histTile[kLag], histTotal[kLag];
+    uint32_t histTile[kLag];
 #pragma unroll
-    for (int h = 0; h < kLag; ++h) { histTile[h] = kNoTile; histTotal[h] = 0u; }
+    for (int h = 0; h < kLag; ++h) histTile[h] = kNoTile;
+    uint32_t slotV = 0u, slotS = 0u;   // ring slots of the tile of iteration j: visibility (mod NV), descriptors (mod kStages)
 
     for (int j = -DV;; ++j) {
         const uint32_t ju = uint32_t(j + 2 * kTileRing * kStages * NV);   // j shifted to a non-negative value with the same residues
@@ -133,29 +135,71 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
         uint32_t ticket = kNoTile;
         if (tid == 0 && s_tiles[(ju + uint32_t(DV)) & (kTileRing - 1)] < p.numTiles) ticket = atomicAdd(&p.ctl->ticket, 1u);
 
-        // ---- step 1, dense: sphere + frustum for the ITEMS objects of this thread; survivors go to the CTA queue ----------
-        cp_async_wait_all();               // everything this thread asked for one and two iterations ago has landed
-        uint32_t survMask = 0u;
+        // ---- step 1, dense: (a) pull this thread's inputs of tile j out of shared memory, (b) immediately re-fill those slots
+        //      with the loads of tiles j+1 / j+2 (a full iteration of lead time), (c) sphere + frustum; survivors -> CTA queue ----
+        cp_async_wait_all();               // everything this thread asked for one iteration ago has landed
+        uint32_t survMask = 0u, visPrevMask = 0u, actMask = 0u;
+        uint2 ob[ITEMS]; float4 ps[ITEMS], qt[ITEMS];
         if (valid) {
             const uint32_t tileBase = tile * uint32_t(TILE);
-            uint32_t visPrevMask = 0u;
-            Sphere sph[ITEMS]; float scl[ITEMS]; uint32_t sid[ITEMS];
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
                 const uint32_t l = localBase + uint32_t(k) * 32u, i = tileBase + l;
                 bool act = i < p.n;
                 if (HAS_VIS) {
-                    const uint32_t vp = visRing[(ju % uint32_t(NV)) * TILE + l];
+                    const uint32_t vp = visRing[slotV * TILE + l];
                     if (act && vp != 0u) visPrevMask |= 1u << k;
                     if (PASS == PASS_EARLY) act = act && (vp != 0u);                     // InitialDrawCull.comp.glsl:21-24
                 }
-                sph[k] = Sphere{ 0.f, 0.f, 0.f, 0.f }; scl[k] = 1.f; sid[k] = 0u;
-                if (act) {
-                    const uint2 ob = objRing[(ju & 1u) * TILE + l];
-                    const float4 ps = xfPS[l], qt = xfQ[l];
-                    const float4 bs = *reinterpret_cast<const float4*>(&surfT[ob.y]);   // {center.xyz, radius}
-                    sid[k] = ob.y; scl[k] = ps.w;
-                    sph[k] = view_space_sphere(bs.x, bs.y, bs.z, bs.w, ps.x, ps.y, ps.z, ps.w, qt.x, qt.y, qt.z, qt.w, V);
+                if (act) actMask |= 1u << k;
+                ob[k] = objRing[(ju & 1u) * TILE + l];
+                ps[k] = xfPS[l]; qt[k] = xfQ[l];
+            }
+        }
+        {
+            const uint32_t slotV1 = slotV + 1u == uint32_t(NV) ? 0u : slotV + 1u;                    // tile j+1
+            const uint32_t slotV2 = slotV1 + 1u == uint32_t(NV) ? 0u : slotV1 + 1u;                  // tile j+2
+            const uint32_t tN = j + 1 >= 0 ? s_tiles[(ju + 1u) & (kTileRing - 1)] : kNoTile;
+            if (tN < p.numTiles) {
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k) {
+                    const uint32_t l = localBase + uint32_t(k) * 32u;
+                    // early pass: only the objects that were visible last frame (a clamped visibility word of the ragged tail belongs to another object)
+                    if (PASS == PASS_EARLY && (visRing[slotV1 * TILE + l] == 0u || tN * uint32_t(TILE) + l >= p.n)) continue;
+                    const uint32_t t = objRing[((ju + 1u) & 1u) * TILE + l].x - p.transformIdBase;
+                    cp_async16(xfPS + l, p.xfPosScale + t);
+                    cp_async16(xfQ + l, p.xfQuat + t);
+                }
+            }
+            const uint32_t tO = j + 2 >= 0 ? s_tiles[(ju + 2u) & (kTileRing - 1)] : kNoTile;
+            if (tO < p.numTiles) {
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k) {
+                    const uint32_t l = localBase + uint32_t(k) * 32u;
+                    if (PASS == PASS_EARLY && (visRing[slotV2 * TILE + l] == 0u || tO * uint32_t(TILE) + l >= p.n)) continue;
+                    cp_async8(objRing + (ju & 1u) * TILE + l, p.objs + min(tO * uint32_t(TILE) + l, nLast));
+                }
+            }
+            if (HAS_VIS) {
+                const uint32_t tV = s_tiles[(ju + uint32_t(DV)) & (kTileRing - 1)];
+                if (tV < p.numTiles) {
+#pragma unroll
+                    for (int k = 0; k < ITEMS; ++k) {
+                        const uint32_t l = localBase + uint32_t(k) * 32u;
+                        cp_async4(visRing + slotV * TILE + l, p.visibility + min(tV * uint32_t(TILE) + l, nLast));
+                    }
+                }
+            }
+            cp_async_commit();
+        }
+        if (valid) {
+            Sphere sph[ITEMS];
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                sph[k] = Sphere{ 0.f, 0.f, 0.f, 0.f };
+                if ((actMask >> k) & 1u) {
+                    const float4 bs = *reinterpret_cast<const float4*>(&surfT[ob[k].y]);   // {center.xyz, radius}
+                    sph[k] = view_space_sphere(bs.x, bs.y, bs.z, bs.w, ps[k].x, ps[k].y, ps[k].z, ps[k].w, qt[k].x, qt[k].y, qt[k].z, qt[k].w, V);
                     if (frustum_test(sph[k], V)) survMask |= 1u << k;
                 }
             }
@@ -172,54 +216,18 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
                     if ((survMask >> k) & 1u) {
                         const uint32_t slot = base + uint32_t(__popc(ball[k] & laneLt));
                         qSphere[slot] = make_float4(sph[k].x, sph[k].y, sph[k].z, sph[k].r);
-                        qMeta[slot] = make_uint2(__float_as_uint(scl[k]), (localBase + uint32_t(k) * 32u) | (((visPrevMask >> k) & 1u) << 16));
-                        qSurf[slot] = sid[k];
+                        qMeta[slot] = make_uint2(__float_as_uint(ps[k].w), (localBase + uint32_t(k) * 32u) | (((visPrevMask >> k) & 1u) << 16));
+                        qSurf[slot] = ob[k].y;
                     }
                     base += uint32_t(__popc(ball[k]));
                 }
             }
         }
-        // ---- re-fill the slots just read: transforms of tile j+1, RenderObject / visibility of tile j+2 (j+DV) -------------
-        {
-            const uint32_t tN = j + 1 >= 0 ? s_tiles[(ju + 1u) & (kTileRing - 1)] : kNoTile;
-            if (tN < p.numTiles) {
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k) {
-                    const uint32_t l = localBase + uint32_t(k) * 32u;
-                    if (PASS == PASS_EARLY && visRing[((ju + 1u) % uint32_t(NV)) * TILE + l] == 0u) continue;
-                    if (PASS == PASS_EARLY && tN * uint32_t(TILE) + l >= p.n) continue;   // the clamped visibility word belongs to another object
-                    const uint32_t t = objRing[((ju + 1u) & 1u) * TILE + l].x - p.transformIdBase;
-                    cp_async16(xfPS + l, p.xfPosScale + t);
-                    cp_async16(xfQ + l, p.xfQuat + t);
-                }
-            }
-            const uint32_t tO = j + 2 >= 0 ? s_tiles[(ju + 2u) & (kTileRing - 1)] : kNoTile;
-            if (tO < p.numTiles) {
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k) {
-                    const uint32_t l = localBase + uint32_t(k) * 32u;
-                    const uint32_t i = min(tO * uint32_t(TILE) + l, nLast);
-                    if (PASS == PASS_EARLY && (visRing[((ju + 2u) % uint32_t(NV)) * TILE + l] == 0u || tO * uint32_t(TILE) + l >= p.n)) continue;
-                    cp_async8(objRing + (ju & 1u) * TILE + l, p.objs + i);
-                }
-            }
-            if (HAS_VIS) {
-                const uint32_t tV = s_tiles[(ju + uint32_t(DV)) & (kTileRing - 1)];
-                if (tV < p.numTiles) {
-#pragma unroll
-                    for (int k = 0; k < ITEMS; ++k) {
-                        const uint32_t l = localBase + uint32_t(k) * 32u;
-                        cp_async4(visRing + (ju % uint32_t(NV)) * TILE + l, p.visibility + min(tV * uint32_t(TILE) + l, nLast));
-                    }
-                }
-            }
-            cp_async_commit();
-        }
-        __syncthreads();   // (S1) queue complete
+        __syncthreads();   // (S1) queue complete; every thread is past step 4 of the previous iteration
 
-        // ---- step 2, sparse: Hi-Z + LOD for the queue entries, one per thread ----------------------------------------------
-        if (valid) {
-            const uint32_t qn = s_qCount;
+        // ---- step 2, sparse: Hi-Z + LOD for the queue entries, one per thread (skipped, with its barrier, when the queue is empty) ----
+        const uint32_t qn = s_qCount;      // uniform: read after S1, reset after S2 / S3
+        if (qn != 0u) {
             for (uint32_t e = tid; e < qn; e += THREADS) {
                 const float4 q = qSphere[e];
                 const uint2 m = qMeta[e];
@@ -241,10 +249,12 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
                 }
                 sRes[m.y & 0xFFFFu] = (visible ? 1u : 0u) | (emit ? 2u : 0u) | (lodId << 2);
             }
+            __syncthreads();   // (S2) results visible
         }
-        __syncthreads();   // (S2) results visible; nobody reads the queue counter any more
 
         // ---- step 3: read the results back, write visibility, rank the emitters, sum the aggregates for the lagging tile ----
+        // thread 0 publishes the ticket it claimed at the top (first read in the next iteration, behind S3) and re-arms the queue
+        // counter (every thread has read it: either behind S2, or it was 0 anyway).
         if (tid == 0) { s_qCount = 0u; s_tiles[(ju + uint32_t(DV) + 1u) & (kTileRing - 1)] = ticket; }
         uint32_t emitMask = 0u, rank[ITEMS], lodSel[ITEMS], running = 0u;
         if (valid) {
@@ -262,7 +272,7 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
             }
             if (lane == 0) s_warpCnt[warp] = running;
         }
-        const uint32_t outTile = histTile[kLag - 1], outTotal = histTotal[kLag - 1];
+        const uint32_t outTile = histTile[kLag - 1];
         if (outTile != kNoTile) {
             uint32_t part = 0u;
             for (uint32_t t = nextRead + tid; t < outTile; t += THREADS) {
@@ -271,50 +281,53 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
                 part += uint32_t(w);
             }
             part = __reduce_add_sync(0xFFFFFFFFu, part);
-            if (lane == 0) s_red[warp] = part;
+            if (lane == 0 && part != 0u) atomicAdd(&s_sum[ju & 1u], part);
         }
-        __syncthreads();   // (S3) warp counts + partial sums visible; descriptor buffer of tile j-kStages is free
+        __syncthreads();   // (S3) warp counts + aggregate sum visible; queue counter no longer read; descriptor buffer of tile j-kStages is free
 
         // ---- step 4: stage this tile's descriptors + publish its aggregate; write out the records of tile j-kLag -------------
-        uint32_t tileTotal = 0u;
         if (valid) {
-            uint32_t warpOff = 0u;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                const uint32_t c = s_warpCnt[w];
-                if (uint32_t(w) < warp) warpOff += c;
-                tileTotal += c;
+            if (warp == 0) {
+                const uint32_t tileTotal = __reduce_add_sync(0xFFFFFFFFu, lane < uint32_t(WARPS) ? s_warpCnt[lane] : 0u);
+                if (lane == 0) {
+                    st_status(p.status + tile, pack_status(epoch, kStateAggregate, tileTotal));
+                    s_totals[ju & 3u] = tileTotal;
+                }
             }
-            if (tid == 0) st_status(p.status + tile, pack_status(epoch, kStateAggregate, tileTotal));
-            uint32_t* st = stage + (ju % uint32_t(kStages)) * TILE;
+            if (emitMask != 0u) {
+                uint32_t warpOff = 0u;
+                for (uint32_t w = 0; w < warp; ++w) warpOff += s_warpCnt[w];
+                uint32_t* st = stage + slotS * TILE;
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k)
-                if ((emitMask >> k) & 1u) st[warpOff + rank[k]] = (localBase + uint32_t(k) * 32u) | (lodSel[k] << kLocalBits);
+                for (int k = 0; k < ITEMS; ++k)
+                    if ((emitMask >> k) & 1u) st[warpOff + rank[k]] = (localBase + uint32_t(k) * 32u) | (lodSel[k] << kLocalBits);
+            }
         }
         if (outTile != kNoTile) {
-            uint64_t sum = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) sum += s_red[w];
-            const uint64_t prefix = cum + sum;                                                  // records before outTile
+            const uint32_t outTotal = s_totals[(ju - uint32_t(kLag)) & 3u];
+            const uint64_t prefix = cum + s_sum[ju & 1u];                                       // records before outTile
             const uint64_t room = prefix < p.capacity ? p.capacity - prefix : 0ull;
             const uint32_t nrec = uint32_t(room < outTotal ? room : outTotal);
-            const uint32_t* st = stage + ((ju + uint32_t(kStages - kLag)) % uint32_t(kStages)) * TILE;   // slot of iteration j - kLag
-            uint2* dst = reinterpret_cast<uint2*>(p.draws + prefix * p.recWords);
-            const uint32_t idBase = p.objectIdBase + outTile * uint32_t(TILE);
-            // {objectId, indexCount} {instanceCount = 1, firstIndex} {vertexOffset = 0, firstInstance = 0} [{pad, pad}]
-            if (p.recWords == 6u) {
-                for (uint32_t w = tid; w < nrec * 3u; w += THREADS) {
-                    const uint32_t r = w / 3u, f = w - r * 3u;
-                    const uint32_t d = st[r];
-                    const uint2 L = *reinterpret_cast<const uint2*>(&lodT[d >> kLocalBits]);    // {indexCount, firstIndex}
-                    st_cs_u2(dst + w, f == 0u ? make_uint2(idBase + (d & (TILE - 1u)), L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
-                }
-            } else {
-                for (uint32_t w = tid; w < nrec * 4u; w += THREADS) {
-                    const uint32_t r = w >> 2, f = w & 3u;
-                    const uint32_t d = st[r];
-                    const uint2 L = *reinterpret_cast<const uint2*>(&lodT[d >> kLocalBits]);
-                    st_cs_u2(dst + w, f == 0u ? make_uint2(idBase + (d & (TILE - 1u)), L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
+            if (nrec != 0u) {
+                const uint32_t slotOut = slotS + uint32_t(kStages - kLag) >= uint32_t(kStages) ? slotS + uint32_t(kStages - kLag) - uint32_t(kStages) : slotS + uint32_t(kStages - kLag);
+                const uint32_t* st = stage + slotOut * TILE;                                    // slot of iteration j - kLag
+                uint2* dst = reinterpret_cast<uint2*>(p.draws + prefix * p.recWords);
+                const uint32_t idBase = p.objectIdBase + outTile * uint32_t(TILE);
+                // {objectId, indexCount} {instanceCount = 1, firstIndex} {vertexOffset = 0, firstInstance = 0} [{pad, pad}]
+                if (p.recWords == 6u) {
+                    for (uint32_t w = tid; w < nrec * 3u; w += THREADS) {
+                        const uint32_t r = w / 3u, f = w - r * 3u;
+                        const uint32_t d = st[r];
+                        const uint2 L = *reinterpret_cast<const uint2*>(&lodT[d >> kLocalBits]);    // {indexCount, firstIndex}
+                        st_cs_u2(dst + w, f == 0u ? make_uint2(idBase + (d & (TILE - 1u)), L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
+                    }
+                } else {
+                    for (uint32_t w = tid; w < nrec * 4u; w += THREADS) {
+                        const uint32_t r = w >> 2, f = w & 3u;
+                        const uint32_t d = st[r];
+                        const uint2 L = *reinterpret_cast<const uint2*>(&lodT[d >> kLocalBits]);
+                        st_cs_u2(dst + w, f == 0u ? make_uint2(idBase + (d & (TILE - 1u)), L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
+                    }
                 }
             }
             if (outTile == p.numTiles - 1u && tid == 0) {                                      // the draw count the indirect draw reads
@@ -325,10 +338,14 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
             cum = prefix + outTotal;
             nextRead = outTile + 1u;
         }
-        // shift the history of staged tiles
+        // bookkeeping for the next iteration.  s_sum[(j+1)&1] was last read in step 4 of iteration j-1 (before S1 of this one) and is
+        // next added to in step 3 of iteration j+1 (behind its S1).
+        if (tid == 0) s_sum[(ju + 1u) & 1u] = 0u;
 #pragma unroll
-        for (int h = kLag - 1; h > 0; --h) { histTile[h] = histTile[h - 1]; histTotal[h] = histTotal[h - 1]; }
-        histTile[0] = valid ? tile : kNoTile; histTotal[0] = tileTotal;
+        for (int h = kLag - 1; h > 0; --h) histTile[h] = histTile[h - 1];
+        histTile[0] = valid ? tile : kNoTile;
+        slotV = slotV + 1u == uint32_t(NV) ? 0u : slotV + 1u;
+        slotS = slotS + 1u == uint32_t(kStages) ? 0u : slotS + 1u;
         if (j >= 0 && !valid) {
             bool pending = false;
 #pragma unroll
