@@ -7,10 +7,11 @@ namespace blz {
 constexpr int kCullThreads = 256;                    // 8 warps per CTA
 constexpr int kCullItems = 4;                        // objects per thread
 constexpr int kCullTile = kCullThreads * kCullItems; // objects per tile (one ticket) of the instancing / cluster kernels
-constexpr int kDrawThreads = 512;                    // draw-cull kernels: 16 warps per CTA, 2 CTAs per SM
+constexpr int kDrawThreads = 512;                    // draw-cull kernels: 16 warps per CTA, 2 CTAs per SM ...
+constexpr int kDrawDenseWarps = 12;                  // ... 12 of them stream objects (sphere + frustum), 4 evaluate the survivor queue (Hi-Z, LOD)
 constexpr int kDrawItems = 2;
-constexpr int kDrawTile = kDrawThreads * kDrawItems;
-constexpr int kCullMinTile = 1024;                   // smallest tile any kernel uses: sizes the per-tile status array
+constexpr int kDrawTile = kDrawDenseWarps * 32 * kDrawItems;   // 768 objects per tile
+constexpr int kCullMinTile = 768;                    // smallest tile any kernel uses: sizes the per-tile status array
 
 struct DrawCullParams {
     // inputs
