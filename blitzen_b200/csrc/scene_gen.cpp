@@ -85,6 +85,9 @@ int blz_scene_generate(int prngMode, uint64_t seed, int prologue, uint32_t nDyna
     for (uint32_t g = 0; g < nGroups; ++g) total += groups[g].count;
     if (first + count > total) return -2;
 
+    // glibc rand() keeps process-global state: restart the stream so that every call yields the reference's scene
+    // (an unseeded process behaves as if srand(1) had been called)
+    if (prngMode == 0) srand(seed ? unsigned(seed) : 1u);
     auto gen_range = [&](uint64_t a, uint64_t b) {
         Rng r{ prngMode, seed * 0xD1342543DE82EF95ull + 0x632BE59BD9B4E019ull, 0 };
         for (uint64_t i = a; i < b; ++i) {

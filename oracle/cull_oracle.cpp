@@ -8,13 +8,17 @@
 // cull compute shaders, one function per shader function / main, each citing the
 // reference file:line it follows (paths relative to /root/reference/src/Renderer).
 // The reference implements this path ONLY as GLSL/HLSL compute shaders; there is
-// no CPU implementation and no test in the reference ("parity unpinned" by the
-// reference's own tests).  The oracle is pinned instead by
+// no CPU implementation and no test in the reference (the reference ships no
+// golden vectors).  The oracle is pinned instead by
 //   (1) inputs produced by the reference's own compiled frontend (oracle/_ref/refscene),
-//   (2) golden outputs obtained by EXECUTING the reference's own GLSL shaders,
-//       compiled with the reference's bundled glslang, in the SPIR-V interpreter
-//       under oracle/spirv_interp (tests/golden/spirv_*.npz), and
+//   (2) golden outputs obtained by EXECUTING the reference's own GLSL shaders --
+//       compiled to SPIR-V with the reference's bundled glslang -- in the interpreter
+//       under oracle/spirv_interp (tests/golden/spirv_golden.npz, tests/test_oracle_golden.py):
+//       every Vulkan cull shader and the pyramid shader, byte-exact, and
 //   (3) hand-derived known-answer tests (tests/test_oracle_kat.py).
+// PARITY UNPINNED for the D3D12-only parts (HlslShaders/CS/*.hlsl: the point-sample
+// OcclusionCheck, the 2x2-min pyramid, indirect instancing): dxc is a Windows binary,
+// so those functions are restatements checked only by (1) and (3).
 //
 // Float rules: strict IEEE-754 binary32, no contraction
 // (-ffp-contract=off, no -ffast-math), evaluation order exactly as written in

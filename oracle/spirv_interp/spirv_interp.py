@@ -515,6 +515,8 @@ class Machine:
 
     def _bitcast(self, tid, v):
         t = self.m.types[tid]
+        if t.kind == "vector" and isinstance(v, list) and len(v) == t.count:   # e.g. uvec2 -> ivec2: component-wise
+            return [self._bitcast(t.elem, x) for x in v]
         if t.kind == "pointer":
             if isinstance(v, MemPtr):
                 return MemPtr(v.buf, v.off, t.pointee)

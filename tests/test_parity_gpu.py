@@ -281,3 +281,70 @@ def test_sharded_ids(capi, small_scene):
             got, _ = ctx.read_draws()
         parts.append(recs_u32(got))
     assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_against_reference_shader_outputs(capi, built, tables):
+    """CUDA path vs tests/golden/spirv_golden.npz: outputs of the reference's OWN shaders (LateDrawCull, InitialDrawCull,
+    TransparentDrawCull, OnpcDrawCull, PreClusterDrawCull, InitialClusterCull, DepthPyramidGeneration) executed by
+    oracle/spirv_interp.  Same order on both sides (ascending id), so equality is exact."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spirv_golden.npz"))
+    views = {str(n): g["views"][i:i + 1] for i, n in enumerate(g["view_names"])}
+    objs, transforms = g["objs"], g["transforms"]
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(objs, transforms, tables["surfaces"], tables["lods"], clusters=tables["clusters"], onpc=g["onpc_objs"],
+                         cluster_dispatch_capacity=len(g["cluster_dispatch_inside"]) + 64)
+        # depth pyramid: DepthPyramidGeneration.comp.glsl
+        ctx.set_depth(g["depth"])
+        ctx.build_pyramid(capi.HIZ_VK)
+        data, whm, offs = ctx.read_pyramid()
+        assert tuple(whm) == tuple(int(x) for x in g["pyramid_whm"])
+        assert np.array_equal(data.view(np.uint32), g["pyramid"].view(np.uint32))
+        for vn in ("inside", "tilted", "all", "ref_default"):
+            ctx.set_view(views[vn])
+            ctx.frustum_lod()
+            got, tot = ctx.read_draws()
+            assert np.array_equal(recs_u32(got), g[f"transparent_{vn}"]), vn
+        for vn in ("inside", "tilted"):
+            ctx.set_view(views[vn])
+            ctx.write_visibility(g["vis0"])
+            ctx.early()
+            got, _ = ctx.read_draws()
+            assert np.array_equal(recs_u32(got), g[f"initial_{vn}"]), vn
+            ctx.late(capi.REC_VK24, capi.HIZ_VK)
+            got, _ = ctx.read_draws()
+            assert np.array_equal(recs_u32(got), g[f"late_{vn}"]), vn
+            assert np.array_equal(ctx.read_visibility(), g[f"late_vis_{vn}"]), vn
+        ctx.set_view(views["inside"])
+        ctx.frustum_lod(capi.LIST_ONPC, capi.REC_VK24, capi.FLAG_ONPC_LOD_QUIRK)
+        got, _ = ctx.read_draws()
+        assert np.array_equal(recs_u32(got), g["onpc_inside"])
+    n = int(g["cluster_objs_count"][0])
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(objs[:n], transforms, tables["surfaces"], tables["lods"], clusters=tables["clusters"],
+                         cluster_dispatch_capacity=len(g["cluster_dispatch_inside"]) + 64, draw_capacity=len(g["cluster_dispatch_inside"]) + 64)
+        ctx.set_view(views["inside"])
+        ctx.cluster_expand()
+        rec, tot = ctx.read_cluster_dispatch()
+        assert np.array_equal(rec.view(np.uint32).reshape(-1, 3), g["cluster_dispatch_inside"])
+        ctx.cluster_cull(capi.CLUSTER_PASSTHROUGH, capi.REC_VK24)
+        got, _ = ctx.read_draws()
+        assert np.array_equal(recs_u32(got), g["cluster_draws_inside"])
+    # the reference's own scene head under the reference's own cameras
+    from blitzen_b200 import sceneio, scene
+    head = sceneio.read_blob(os.path.join(os.path.dirname(__file__), "golden", "stress_head_4k.blob"))
+    rviews = scene.reference_views()
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(head["objs"], head["transforms"], head["surfaces"], head["lods"])
+        ctx.set_depth(g["depth"])
+        ctx.build_pyramid(capi.HIZ_VK)
+        for vn in ("default", "cfg1_centre", "cfg1_tilted", "cfg1_all"):
+            ctx.set_view(rviews[vn])
+            ctx.frustum_lod()
+            got, _ = ctx.read_draws()
+            assert np.array_equal(recs_u32(got), g[f"head_transparent_{vn}"]), vn
+            ctx.write_visibility(g["head_vis0"])
+            ctx.late(capi.REC_VK24, capi.HIZ_VK)
+            got, _ = ctx.read_draws()
+            assert np.array_equal(recs_u32(got), g[f"head_late_{vn}"]), vn
+            assert np.array_equal(ctx.read_visibility(), g[f"head_late_vis_{vn}"]), vn
