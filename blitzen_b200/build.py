@@ -49,6 +49,7 @@ def _stale(target, deps):
 def build_cull(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     deps = srcs + [os.path.normpath(os.path.join(CSRC, h)) for h in CUDA_HEADERS] + [os.path.abspath(__file__)]
+    deps += [os.path.join(PKG, "host", f) for f in ("blitzenCudaCull.cpp", "blitzenCudaCull.h")]
     if not force and not _stale(LIB_CULL, deps):
         return LIB_CULL
     objdir = os.path.join(PKG, "build")
@@ -73,7 +74,12 @@ def build_cull(force=False, verbose=False):
             sys.stderr.write(text)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    subprocess.run([nvcc, "-shared", "-o", LIB_CULL, *objs, "-cudart", "static", "-Xlinker", "--no-undefined"], check=True)
+    # the C++ host class above the C ABI (host/blitzenCudaCull.cpp) ships in the same library
+    host_o = os.path.join(objdir, "blitzenCudaCull.o")
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    subprocess.run([cxx, "-std=c++17", "-O2", "-fPIC", "-c", os.path.join(PKG, "host", "blitzenCudaCull.cpp"), "-o", host_o], check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_CULL, *objs, host_o, "-cudart", "static",
+                    "-Xlinker", "--no-undefined"], check=True)
     return LIB_CULL
 
 
