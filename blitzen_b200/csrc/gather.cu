@@ -15,7 +15,13 @@ namespace blz {
 namespace {
 
 constexpr int kGatherThreads = 256;
-constexpr int kFlagStride = 64;      // count words at [0, 64), done words at [64, 128)
+constexpr int kFlagStride = 64;      // ranks per row
+constexpr int kEpochSlots = 4;       // count words of epoch e live in row e % 4: rows [0, 4); done words in row 4
+constexpr int kDoneRow = kEpochSlots;
+constexpr int kFlagWords = (kEpochSlots + 1) * kFlagStride;
+// Epochs are consecutive integers starting at 1.  A rank may run ahead of a slower one (nothing on the host orders the
+// pushes of different ranks), so the count words are kept per epoch in a ring of 4 rows and a rank does not publish epoch e
+// before every rank has finished epoch e - 3: a word is never overwritten while somebody still waits for it.
 
 __device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p)
@@ -30,7 +36,7 @@ struct GatherParams {
     uint32_t* dst; uint64_t* flags;                  // presenter's buffer + flag block (peer-mapped, or local on the presenter)
     uint32_t* done;                                  // local CTA-completion counter (self-resetting)
     uint64_t capacity;                               // records the presenter's buffer holds
-    uint32_t recWords, rank, epoch;
+    uint32_t recWords, rank, world, epoch;
 };
 
 __global__ void __launch_bounds__(kGatherThreads) gather_push_kernel(const GatherParams p)
@@ -40,11 +46,17 @@ __global__ void __launch_bounds__(kGatherThreads) gather_push_kernel(const Gathe
     uint32_t count;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(count) : "l"(p.srcCount));
     if (tid == 0) {
-        if (blockIdx.x == 0) st_release_sys_u64(p.flags + p.rank, (uint64_t(p.epoch) << 32) | count);
+        uint64_t* row = p.flags + (p.epoch % uint32_t(kEpochSlots)) * kFlagStride;
+        if (blockIdx.x == 0) {
+            if (p.epoch > uint32_t(kEpochSlots - 1))                       // back-pressure: everybody is done with epoch e - 3
+                for (uint32_t r = 0; r < p.world; ++r)
+                    while (int32_t(uint32_t(ld_acquire_sys_u64(p.flags + kDoneRow * kFlagStride + r)) - (p.epoch - uint32_t(kEpochSlots - 1))) < 0) { }
+            st_release_sys_u64(row + p.rank, (uint64_t(p.epoch) << 32) | count);
+        }
         uint64_t off = 0;
         for (uint32_t r = 0; r < p.rank; ++r) {
             uint64_t w;
-            do { w = ld_acquire_sys_u64(p.flags + r); } while (uint32_t(w >> 32) != p.epoch);
+            do { w = ld_acquire_sys_u64(row + r); } while (uint32_t(w >> 32) != p.epoch);
             off += uint32_t(w);
         }
         s_off = off;
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_push_kernel(const Gathe
         const uint32_t prev = atomicAdd(p.done, 1u);
         if (prev == gridDim.x - 1u) {
             *p.done = 0u;
-            st_release_sys_u64(p.flags + kFlagStride + p.rank, uint64_t(p.epoch));
+            st_release_sys_u64(p.flags + kDoneRow * kFlagStride + p.rank, uint64_t(p.epoch));
         }
     }
 }
@@ -71,7 +83,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_push_kernel(const Gathe
 __global__ void gather_wait_kernel(const uint64_t* flags, uint32_t world, uint32_t epoch)
 {
     const uint32_t r = threadIdx.x;
-    if (r < world) { while (uint32_t(ld_acquire_sys_u64(flags + kFlagStride + r)) != epoch) { } }
+    if (r < world) { while (int32_t(uint32_t(ld_acquire_sys_u64(flags + kDoneRow * kFlagStride + r)) - epoch) < 0) { } }
 }
 
 } // namespace
@@ -103,8 +115,8 @@ int blz_cull_gather_export(blz_cull_ctx* c, uint64_t capacityRecords, int fmt, v
     c->gatherRecWords = fmt == BLZ_REC_VK24 ? 6u : 8u;
     c->gatherCap = capacityRecords;
     CU_TRY(cudaMalloc(&c->gatherBuf, size_t(capacityRecords) * c->gatherRecWords * 4u));
-    CU_TRY(cudaMalloc(&c->gatherFlags, 2 * kFlagStride * sizeof(uint64_t)));
-    CU_TRY(cudaMemset(c->gatherFlags, 0, 2 * kFlagStride * sizeof(uint64_t)));
+    CU_TRY(cudaMalloc(&c->gatherFlags, kFlagWords * sizeof(uint64_t)));
+    CU_TRY(cudaMemset(c->gatherFlags, 0, kFlagWords * sizeof(uint64_t)));
     c->gatherOwner = true;
     cudaIpcMemHandle_t h[2];
     CU_TRY(cudaIpcGetMemHandle(&h[0], c->gatherBuf));
@@ -156,7 +168,7 @@ int blz_cull_gather_push(blz_cull_ctx* c, uint32_t epoch)
     CU_TRY(cudaSetDevice(c->device));
     GatherParams p{};
     p.src = c->draws; p.srcCount = c->counts; p.dst = c->gatherDst; p.flags = c->gatherDstFlags; p.done = c->gatherDone;
-    p.capacity = c->gatherCap; p.recWords = c->gatherRecWords; p.rank = uint32_t(c->rank); p.epoch = epoch;
+    p.capacity = c->gatherCap; p.recWords = c->gatherRecWords; p.rank = uint32_t(c->rank); p.world = uint32_t(c->world); p.epoch = epoch;
     gather_push_kernel<<<c->numSMs * 2, kGatherThreads, 0, c->stream>>>(p);
     CU_TRY(cudaGetLastError());
     c->launches++;
@@ -171,7 +183,7 @@ int blz_cull_gather_read(blz_cull_ctx* c, uint32_t epoch, void* recordsHost, uin
     CU_TRY(cudaGetLastError());
     c->launches++;
     uint64_t flags[kFlagStride];
-    CU_TRY(cudaMemcpyAsync(flags, c->gatherFlags, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(flags, c->gatherFlags + (epoch % uint32_t(kEpochSlots)) * kFlagStride, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     uint64_t total = 0;
     for (int r = 0; r < c->world; ++r) { if (outCounts) outCounts[r] = uint32_t(flags[r]); total += uint32_t(flags[r]); }

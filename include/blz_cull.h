@@ -185,7 +185,10 @@ int blz_cull_read_pyramid(blz_cull_ctx* ctx, float* pyramid_host, uint64_t capac
  *   blz_cull_gather_import : maps the presenter's blobs, records (rank, world)
  *   blz_cull_gather_push   : after a cull pass, ONE kernel publishes this rank's count to the presenter's flag block, waits for
  *                            the lower ranks' counts (exclusive scan) and stores this rank's records into the presenter's
- *                            gather buffer at that offset over NVLink peer memory.  No NCCL call on the data path. */
+ *                            gather buffer at that offset over NVLink peer memory.  No NCCL call on the data path.
+ *                            `epoch` = 1, 2, 3, ... (consecutive, the same sequence on every rank).  Ranks need no host-side
+ *                            ordering between pushes: counts are kept per epoch in a ring of 4 and a rank stalls (on the
+ *                            device) rather than run more than 3 epochs ahead of the slowest one. */
 int blz_cull_gather_export(blz_cull_ctx* ctx, uint64_t capacity_records, int record_format, void* out_blob128);
 int blz_cull_gather_import(blz_cull_ctx* ctx, const void* presenter_blob128, int rank, int world);
 /* ranks that did not export learn the presenter buffer's capacity / record format from the host layer */
