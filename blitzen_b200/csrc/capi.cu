@@ -170,7 +170,10 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.capacity = c->drawCap;
     p.view = make_view_consts(c->view);
     p.pyr = c->pyr;
-    CU_TRY(launch_draw_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
+    // early pass: the sparse kernel (one 4-B stream + a gather for the objects that were visible) unless told otherwise;
+    // option early_mode: 0 = pipelined kernel, 1 = sparse kernel (default)
+    if (pass == PASS_EARLY && c->optEarlyMode == 1 && p.lodCount < (1u << 20)) CU_TRY(launch_early_sparse(p, c->stream));
+    else CU_TRY(launch_draw_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
     c->launches++;
     c->lastRecWords = p.recWords;
     return BLZ_OK;
@@ -654,6 +657,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
 {
     if (!c || !name) return fail(BLZ_ERR_INVALID, "null argument");
     if (strcmp(name, "pyramid_tma") == 0) { c->optPyramidTma = value; return BLZ_OK; }
+    if (strcmp(name, "early_mode") == 0) { c->optEarlyMode = value; return BLZ_OK; }
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);
 }
 

@@ -40,6 +40,7 @@ struct blz_cull_ctx {
     blz::CameraViewData view{}; bool haveView = false;
     uint64_t launches = 0;
     int64_t optPyramidTma = 1;
+    int64_t optEarlyMode = 1;
     uint32_t lastRecWords = 6;                // record width (u32 words) of the pass that last wrote `draws`
     // gather (multi-GPU): the presenter owns gatherBuf/gatherFlags; every rank (presenter included) writes through gatherDst*
     uint32_t* gatherBuf = nullptr; uint64_t gatherCap = 0; uint32_t gatherRecWords = 6; uint64_t* gatherFlags = nullptr; bool gatherOwner = false;

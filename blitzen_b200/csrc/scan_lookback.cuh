@@ -61,6 +61,55 @@ __device__ __forceinline__ uint32_t lookback_exclusive_prefix(uint64_t* status, 
     return exclusive;
 }
 
+// CTA-wide variant: every thread of the CTA (THREADS = blockDim.x, a multiple of 32) calls it; windows of THREADS predecessors
+// per step instead of 32.  One-shot CTAs that all finish at about the same time would otherwise walk back over every
+// concurrently running tile 32 at a time (an L2 round trip per step).  `scratch` = 2 * THREADS / 32 + 2 shared words.
+// Returns the exclusive prefix to all threads; contains __syncthreads().
+template <int THREADS>
+__device__ __forceinline__ uint32_t lookback_exclusive_prefix_cta(uint64_t* status, uint32_t tile, uint32_t aggregate, uint32_t epoch, uint32_t* scratch)
+{
+    constexpr int WARPS = THREADS / 32;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    epoch &= 0x3FFFFFFFu;
+    uint32_t* s_first = scratch;            // per warp: lane of the nearest inclusive predecessor, 32 = none
+    uint32_t* s_sum = scratch + WARPS;      // per warp: sum up to and including that lane (or of all 32)
+    uint32_t* s_out = scratch + 2 * WARPS;  // [0] = running exclusive prefix, [1] = done flag
+    if (tile == 0) {
+        if (tid == 0) st_status(status, pack_status(epoch, kStateInclusive, aggregate));
+        return 0u;
+    }
+    if (tid == 0) { st_status(status + tile, pack_status(epoch, kStateAggregate, aggregate)); s_out[0] = 0u; s_out[1] = 0u; }
+    int64_t base = int64_t(tile);           // predecessors [base - THREADS, base) are examined in this step, nearest first
+    while (true) {
+        const int64_t look = base - 1 - int64_t(tid);
+        uint32_t state = kStateInclusive, value = 0;              // virtual tiles before tile 0: inclusive prefix 0
+        if (look >= 0) {
+            uint64_t w;
+            do { w = ld_status(status + look); } while (uint32_t(w >> 34) != epoch || (uint32_t(w >> 32) & 3u) == 0u);
+            state = uint32_t(w >> 32) & 3u;
+            value = uint32_t(w);
+        }
+        const uint32_t inclMask = __ballot_sync(0xFFFFFFFFu, state == kStateInclusive);
+        const uint32_t first = inclMask ? uint32_t(__ffs(int(inclMask))) - 1u : 32u;
+        const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, lane <= first ? value : 0u);
+        if (lane == 0) { s_first[warp] = first; s_sum[warp] = sum; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t acc = s_out[0];
+            bool found = false;
+            for (int w = 0; w < WARPS && !found; ++w) { acc += s_sum[w]; found = s_first[w] < 32u; }
+            s_out[0] = acc; s_out[1] = found ? 1u : 0u;
+        }
+        __syncthreads();
+        if (s_out[1] != 0u) break;
+        base -= THREADS;
+        __syncthreads();                                           // s_out[1] read by everybody before thread 0 rewrites it
+    }
+    const uint32_t exclusive = s_out[0];
+    if (tid == 0) st_status(status + tile, pack_status(epoch, kStateInclusive, exclusive + aggregate));
+    return exclusive;
+}
+
 // Serial variant used by one THREAD per independent chain (the per-LOD chains of the instancing pass): chain c of tile t
 // lives at status[t * stride + c].
 __device__ __forceinline__ uint32_t lookback_exclusive_prefix_serial(uint64_t* status, uint32_t stride, uint32_t chain, uint32_t tile,
