@@ -170,10 +170,14 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.capacity = c->drawCap;
     p.view = make_view_consts(c->view);
     p.pyr = c->pyr;
-    // early pass: the sparse kernel (one 4-B stream + a gather for the objects that were visible) unless told otherwise;
-    // option early_mode: 0 = pipelined kernel, 1 = sparse kernel (default)
-    if (pass == PASS_EARLY && c->optEarlyMode == 1 && p.lodCount < (1u << 20)) CU_TRY(launch_early_sparse(p, c->stream));
+    // The late pass leaves the ascending list of the ids it marked visible; as long as nothing else writes visibility[] the next
+    // early pass culls that list instead of streaming over all N objects.  Otherwise: the sparse kernel (4-B visibility stream +
+    // gather for the visible ones).  option early_mode: 0 = pipelined kernel, 1 = sparse kernel, 2 = list when valid (default).
+    p.visList = c->visList; p.visCount = c->counts + 4;
+    if (pass == PASS_EARLY && c->optEarlyMode == 2 && c->visListValid) CU_TRY(launch_early_list(p, c->numSMs, c->stream));
+    else if (pass == PASS_EARLY && c->optEarlyMode >= 1 && p.lodCount < (1u << 20)) CU_TRY(launch_early_sparse(p, c->stream));
     else CU_TRY(launch_draw_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
+    if (pass == PASS_LATE) c->visListValid = true;
     c->launches++;
     c->lastRecWords = p.recWords;
     return BLZ_OK;
@@ -207,8 +211,8 @@ int blz_cull_create(int device, blz_cull_ctx** out)
     CU_TRY(cudaMalloc(&c->ctl, sizeof(ScanCtl)));
     ScanCtl init{ 0u, 0u, 1u, 0u };
     CU_TRY(cudaMemcpyAsync(c->ctl, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(cudaMalloc(&c->counts, 4 * sizeof(uint32_t)));
-    CU_TRY(cudaMemsetAsync(c->counts, 0, 4 * sizeof(uint32_t), c->stream));
+    CU_TRY(cudaMalloc(&c->counts, 8 * sizeof(uint32_t)));
+    CU_TRY(cudaMemsetAsync(c->counts, 0, 8 * sizeof(uint32_t), c->stream));
     CU_TRY(cudaMalloc(&c->pyrTicket, sizeof(uint32_t)));
     CU_TRY(cudaMemsetAsync(c->pyrTicket, 0, sizeof(uint32_t), c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -221,7 +225,8 @@ static void free_scene(blz_cull_ctx* c)
     for (int i = 0; i < 3; ++i) { dfree(c->objs[i]); c->nObjs[i] = 0; }
     dfree(c->xfPS); dfree(c->xfQ); dfree(c->xfStage); c->nXf = 0; c->xfStageCap = 0;
     dfree(c->surf); dfree(c->lods); dfree(c->clusters); dfree(c->lodInst); dfree(c->bucketCap);
-    dfree(c->vis); dfree(c->draws); dfree(c->dispatch); dfree(c->instIdx);
+    dfree(c->vis); dfree(c->visList); dfree(c->draws); dfree(c->dispatch); dfree(c->instIdx);
+    c->capVisList = 0; c->visListValid = false;
     c->nSurf = c->nLods = c->nClusters = c->nLodInst = 0; c->drawCap = c->dispatchCap = c->instCap = 0;
     c->capObjs[0] = c->capObjs[1] = c->capObjs[2] = 0;
     c->capXfPS = c->capXfQ = c->capSurf = c->capLods = c->capClusters = c->capLodInst = c->capBucket = 0;
@@ -316,6 +321,8 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     const size_t nVis = c->nObjs[0] ? c->nObjs[0] : 1;
     TRY_RC(grow(c, c->vis, c->capVis, nVis * sizeof(uint32_t)));
     CU_TRY(cudaMemsetAsync(c->vis, 0, nVis * sizeof(uint32_t), c->stream));
+    TRY_RC(grow(c, c->visList, c->capVisList, nVis * sizeof(uint32_t)));
+    c->visListValid = false;
     // draw buffer (sized for the wider DX32 record), cluster dispatch buffer
     c->drawCap = d->draw_capacity ? d->draw_capacity : (maxList ? maxList : 1);
     TRY_RC(grow(c, c->draws, c->capDraws, size_t(c->drawCap) * 8u * sizeof(uint32_t)));
@@ -388,6 +395,7 @@ int blz_cull_reset_visibility(blz_cull_ctx* c)
     if (!c || !c->vis) return fail(BLZ_ERR_INVALID, "no scene uploaded");
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMemsetAsync(c->vis, 0, size_t(c->nObjs[0] ? c->nObjs[0] : 1) * sizeof(uint32_t), c->stream));
+    c->visListValid = false;
     return BLZ_OK;
 }
 
@@ -397,6 +405,7 @@ int blz_cull_write_visibility(blz_cull_ctx* c, const uint32_t* host)
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMemcpyAsync(c->vis, host, size_t(c->nObjs[0]) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    c->visListValid = false;
     return BLZ_OK;
 }
 

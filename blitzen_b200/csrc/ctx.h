@@ -24,7 +24,9 @@ struct blz_cull_ctx {
     // per-object state + outputs
     uint32_t* vis = nullptr;
     uint32_t* draws = nullptr; uint64_t drawCap = 0;
-    uint32_t* counts = nullptr;               // [0..1] draws, [2..3] cluster dispatch
+    uint32_t* counts = nullptr;               // [0..1] draws, [2..3] cluster dispatch, [4] length of visList
+    uint32_t* visList = nullptr; size_t capVisList = 0;   // ascending ids the last late pass found visible
+    bool visListValid = false;                // true while visibility[] has not been written by anything but that late pass
     uint32_t* dispatch = nullptr; uint64_t dispatchCap = 0;
     uint32_t* instIdx = nullptr; uint64_t instCap = 0;
     blz::ScanCtl* ctl = nullptr;
@@ -40,7 +42,7 @@ struct blz_cull_ctx {
     blz::CameraViewData view{}; bool haveView = false;
     uint64_t launches = 0;
     int64_t optPyramidTma = 1;
-    int64_t optEarlyMode = 1;
+    int64_t optEarlyMode = 2;                 // 0 = pipelined kernel, 1 = sparse (visibility stream) kernel, 2 = visible list when valid, else sparse
     uint32_t lastRecWords = 6;                // record width (u32 words) of the pass that last wrote `draws`
     // gather (multi-GPU): the presenter owns gatherBuf/gatherFlags; every rank (presenter included) writes through gatherDst*
     uint32_t* gatherBuf = nullptr; uint64_t gatherCap = 0; uint32_t gatherRecWords = 6; uint64_t* gatherFlags = nullptr; bool gatherOwner = false;

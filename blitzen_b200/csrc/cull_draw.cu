@@ -102,14 +102,15 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
 {
     constexpr int ITEMS = kDrawItems, TILE = kDrawTile, THREADS = kDrawThreads, DWARPS = kDrawDenseWarps, DTHREADS = DWARPS * 32;
     constexpr bool HAS_VIS = (PASS == PASS_EARLY || PASS == PASS_LATE);
+    constexpr bool VIS_LIST = (PASS == PASS_LATE);       // the late pass also emits the ascending list of visible ids: next frame's early pass
     constexpr int DV = (PASS == PASS_EARLY) ? 3 : 2;     // prefetch distance of the visibility words (the early pass needs them to ask for objects)
     constexpr int NV = DV;                                // ring depth: the slot of tile j is re-filled with tile j+DV right after it is read
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_tiles[kTileRing];
-    __shared__ uint32_t s_warpCnt[DWARPS];
-    __shared__ uint32_t s_totals[4];       // emit count of the tile finished in iteration j, at [j & 3]
-    __shared__ uint32_t s_sum[2];          // sum of the aggregates between this CTA's consecutive tiles, at [j & 1]
+    __shared__ uint32_t s_warpCnt[DWARPS], s_warpCntV[DWARPS];
+    __shared__ uint32_t s_totals[4];       // emit count | visible count << 16 of the tile finished in iteration j, at [j & 3]
+    __shared__ uint32_t s_sum[2], s_sumV[2];   // sums of the aggregates (emitters / visible) between this CTA's consecutive tiles, at [j & 1]
     __shared__ uint32_t s_qCount[2];       // entries pushed into queue [j & 1] by the dense step of iteration j
     __shared__ uint32_t s_qHead[2];        // next unclaimed batch of that queue
 
@@ -140,7 +141,8 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
     uint32_t* qSurfB = reinterpret_cast<uint32_t*>(sp);    sp += size_t(2) * TILE * sizeof(uint32_t);  //   surfaceId
     uint32_t* sResB = reinterpret_cast<uint32_t*>(sp);     sp += size_t(2) * TILE * sizeof(uint32_t);  // visible | emit << 1 | lodId << 2, per object of the tile
     uint32_t* stage = reinterpret_cast<uint32_t*>(sp);     sp += size_t(kStages) * TILE * sizeof(uint32_t);
-    uint32_t* visRing = reinterpret_cast<uint32_t*>(sp);   // NV * TILE words (only when HAS_VIS)
+    uint32_t* visRing = reinterpret_cast<uint32_t*>(sp);   sp += HAS_VIS ? size_t(NV) * TILE * sizeof(uint32_t) : 0;
+    uint16_t* stageV = reinterpret_cast<uint16_t*>(sp);    // kStages * TILE index-in-tile of the visible objects (late pass only)
 
     const uint32_t epoch = ld_cg_u32(&p.ctl->epoch) & 0x3FFFFFFFu;   // constant for the whole launch (the last CTA out bumps it)
     const ViewConsts& V = p.view;
@@ -149,11 +151,11 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
 
     if (tid == 0) {
         s_tiles[0] = atomicAdd(&p.ctl->ticket, 1u);
-        s_qCount[0] = s_qCount[1] = 0u; s_qHead[0] = s_qHead[1] = 0u; s_sum[0] = s_sum[1] = 0u;
+        s_qCount[0] = s_qCount[1] = 0u; s_qHead[0] = s_qHead[1] = 0u; s_sum[0] = s_sum[1] = 0u; s_sumV[0] = s_sumV[1] = 0u;
     }
     __syncthreads();     // first tile + tables visible
 
-    uint64_t cum = 0;                  // records emitted by tiles [0, nextRead)
+    uint64_t cum = 0, cumV = 0;        // records emitted by / visible objects of tiles [0, nextRead)
     uint32_t nextRead = 0;             // first tile whose aggregate this CTA has not summed yet
     uint32_t histTile[kLag + 1];       // [0] = tile of iteration j-1 (its queue is evaluated during iteration j-1 .. j), [kLag] = tile whose records go out now
 #pragma unroll
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
             // of the queue that iteration j+1 fills (drained before this X, pushed to after the dense-warp barrier below)
             if (tid == 0) { s_qCount[qb ^ 1u] = 0u; s_qHead[qb ^ 1u] = 0u; s_tiles[(ju + uint32_t(DV) + 1u) & (kTileRing - 1)] = ticket; }
             uint32_t emitMask = 0u, rank[ITEMS], lodSel[ITEMS], running = 0u;
+            uint32_t visMask = 0u, rankV[ITEMS], runningV = 0u;
             if (postTile != kNoTile) {
                 const uint32_t* res = sResB + (qb ^ 1u) * TILE;
 #pragma unroll
@@ -287,29 +290,49 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
                     const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, emit);
                     rank[k] = running + uint32_t(__popc(ballot & laneLt));
                     running += uint32_t(__popc(ballot));
+                    if (VIS_LIST) {
+                        const uint32_t bv = __ballot_sync(0xFFFFFFFFu, (r & 1u) != 0u);
+                        visMask |= (r & 1u) << k;
+                        rankV[k] = runningV + uint32_t(__popc(bv & laneLt));
+                        runningV += uint32_t(__popc(bv));
+                    }
                 }
-                if (lane == 0) s_warpCnt[warp] = running;
+                if (lane == 0) { s_warpCnt[warp] = running; if (VIS_LIST) s_warpCntV[warp] = runningV; }
             }
             if (outTile != kNoTile) {
-                uint32_t part = 0u;
+                uint32_t part = 0u, partV = 0u;                     // a tile's aggregate word: emitters | visible << 16 (both <= TILE)
                 for (uint32_t t = nextRead + tid; t < outTile; t += DTHREADS) {
                     uint64_t w;
                     do { w = ld_status(p.status + t); } while (uint32_t(w >> 34) != epoch || (uint32_t(w >> 32) & 3u) == 0u);
-                    part += uint32_t(w);
+                    part += uint32_t(w) & 0xFFFFu;
+                    if (VIS_LIST) partV += uint32_t(w) >> 16;
                 }
                 part = __reduce_add_sync(0xFFFFFFFFu, part);
                 if (lane == 0 && part != 0u) atomicAdd(&s_sum[ju & 1u], part);
+                if (VIS_LIST) {
+                    partV = __reduce_add_sync(0xFFFFFFFFu, partV);
+                    if (lane == 0 && partV != 0u) atomicAdd(&s_sumV[ju & 1u], partV);
+                }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(DTHREADS) : "memory");   // dense warps only: warp counts + aggregate sum visible
 
             // ---- D3: stage tile j-1's descriptors + publish its aggregate; write out the records of the tile finished kLag iterations ago ----
             if (postTile != kNoTile) {
                 if (warp == 0) {
-                    const uint32_t tileTotal = __reduce_add_sync(0xFFFFFFFFu, lane < uint32_t(DWARPS) ? s_warpCnt[lane] : 0u);
+                    uint32_t tileTotal = __reduce_add_sync(0xFFFFFFFFu, lane < uint32_t(DWARPS) ? s_warpCnt[lane] : 0u);
+                    if (VIS_LIST) tileTotal |= __reduce_add_sync(0xFFFFFFFFu, lane < uint32_t(DWARPS) ? s_warpCntV[lane] : 0u) << 16;
                     if (lane == 0) {
                         st_status(p.status + postTile, pack_status(epoch, kStateAggregate, tileTotal));
                         s_totals[ju & 3u] = tileTotal;
                     }
+                }
+                if (VIS_LIST && visMask != 0u) {
+                    uint32_t warpOffV = 0u;
+                    for (uint32_t w = 0; w < warp; ++w) warpOffV += s_warpCntV[w];
+                    uint16_t* sv = stageV + slotS * TILE;
+#pragma unroll
+                    for (int k = 0; k < ITEMS; ++k)
+                        if ((visMask >> k) & 1u) sv[warpOffV + rankV[k]] = uint16_t(localBase + uint32_t(k) * 32u);
                 }
                 if (emitMask != 0u) {
                     uint32_t warpOff = 0u;
@@ -321,12 +344,23 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
                 }
             }
             if (outTile != kNoTile) {
-                const uint32_t outTotal = s_totals[(ju - uint32_t(kLag)) & 3u];
+                const uint32_t outPacked = s_totals[(ju - uint32_t(kLag)) & 3u];
+                const uint32_t outTotal = outPacked & 0xFFFFu, outVis = outPacked >> 16;
                 const uint64_t prefix = cum + s_sum[ju & 1u];                                       // records before outTile
                 const uint64_t room = prefix < p.capacity ? p.capacity - prefix : 0ull;
                 const uint32_t nrec = uint32_t(room < outTotal ? room : outTotal);
+                const uint32_t slotOut = slotS + uint32_t(kStages - kLag) >= uint32_t(kStages) ? slotS + uint32_t(kStages - kLag) - uint32_t(kStages) : slotS + uint32_t(kStages - kLag);
+                if (VIS_LIST) {
+                    const uint64_t prefixV = cumV + s_sumV[ju & 1u];                                // visible objects before outTile
+                    if (p.visList != nullptr) {
+                        const uint16_t* sv = stageV + slotOut * TILE;
+                        const uint32_t idBaseV = outTile * uint32_t(TILE);                          // LOCAL object index (what the early pass indexes with)
+                        for (uint32_t w = tid; w < outVis; w += DTHREADS) p.visList[prefixV + w] = idBaseV + sv[w];
+                        if (outTile == p.numTiles - 1u && tid == 0) *p.visCount = uint32_t(prefixV + outVis);
+                    }
+                    cumV = prefixV + outVis;
+                }
                 if (nrec != 0u) {
-                    const uint32_t slotOut = slotS + uint32_t(kStages - kLag) >= uint32_t(kStages) ? slotS + uint32_t(kStages - kLag) - uint32_t(kStages) : slotS + uint32_t(kStages - kLag);
                     const uint32_t* st = stage + slotOut * TILE;                                    // slot of iteration j - kLag
                     uint2* dst = reinterpret_cast<uint2*>(p.draws + prefix * p.recWords);
                     const uint32_t idBase = p.objectIdBase + outTile * uint32_t(TILE);
@@ -356,7 +390,7 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
                 nextRead = outTile + 1u;
             }
             // s_sum[(j+1)&1] was last read in D3 of iteration j-1 (before this iteration's X) and is next added to in D2 of iteration j+1 (behind its X)
-            if (tid == 0) s_sum[(ju + 1u) & 1u] = 0u;
+            if (tid == 0) { s_sum[(ju + 1u) & 1u] = 0u; s_sumV[(ju + 1u) & 1u] = 0u; }
         }
         // ---- S / D4: evaluate the queue of tile j in batches of 32 entries, full warps.  The sparse warps start right behind X, so with a
         //      handful of survivors per tile this overlaps D2/D3 and the dense step of tile j+1; dense warps join when there is a backlog. ----
@@ -386,7 +420,7 @@ __global__ void __launch_bounds__(kDrawThreads, 2) draw_cull_kernel(const __grid
     }
 
     cp_async_wait_all();
-    if (p.n == 0u && blockIdx.x == 0 && tid == 0) { p.counts[0] = 0u; p.counts[1] = 0u; }
+    if (p.n == 0u && blockIdx.x == 0 && tid == 0) { p.counts[0] = 0u; p.counts[1] = 0u; if (VIS_LIST && p.visCount) *p.visCount = 0u; }
     // last CTA out re-arms the control block for the next launch on this stream
     if (tid == 0) {
         __threadfence();
@@ -412,6 +446,7 @@ static size_t draw_smem_bytes(int pass, bool smemTables, const DrawCullParams& p
     b += 2 * tile * 4;                 // per-object results of the sparse step
     b += size_t(kStages) * tile * 4;   // survivor descriptors
     if (hasVis) b += nv * tile * 4;
+    if (pass == PASS_LATE) b += size_t(kStages) * tile * 2;   // visible-id descriptors
     return b;
 }
 

@@ -173,6 +173,132 @@ __global__ void __launch_bounds__(kEarlyThreads, 6) early_sparse_kernel(const __
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Early pass over the late pass's visible list.  The only writer of the visibility buffer is the late pass
+// (LateDrawCull.comp.glsl:70), and cull_draw.cu's PASS_LATE kernel emits, next to visibility[], the ascending list of the ids
+// it set to 1.  While nothing else has touched visibility[] since (the C-ABI layer tracks that), "if (visibility[i] == 0)
+// return" is the same as "i is in the list", and the early pass needs no stream over N objects at all: v * (4 + 40) bytes
+// instead of N * 4 + v * 40.  Persistent CTAs, tiles of 512 list entries (two per thread, both gathers in flight together),
+// deterministic order (list order == ascending id), CTA-wide decoupled look-back.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int kListThreads = 256;
+constexpr int kListItems = 2;
+constexpr int kListTile = kListThreads * kListItems;
+
+__global__ void __launch_bounds__(kListThreads, 6) early_list_kernel(const __grid_constant__ DrawCullParams p)
+{
+    constexpr int WARPS = kListThreads / 32;
+    __shared__ uint2 s_desc[kListTile];             // survivors: {local object index, lodId}
+    __shared__ uint32_t s_cnt[kListItems * WARPS];
+    __shared__ uint32_t s_scratch[2 * WARPS + 2];
+    __shared__ uint32_t s_tile;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t laneLt = (1u << lane) - 1u;
+    const ViewConsts& V = p.view;
+    uint32_t epoch, v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(epoch) : "l"(&p.ctl->epoch));
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p.visCount));
+    const uint32_t numTiles = (v + uint32_t(kListTile) - 1u) / uint32_t(kListTile);
+    if (v == 0u && blockIdx.x == 0 && tid == 0) { p.counts[0] = 0u; p.counts[1] = 0u; }
+
+    while (true) {
+        __syncthreads();                                                          // previous tile fully written out (s_desc, s_tile reuse)
+        if (tid == 0) s_tile = atomicAdd(&p.ctl->ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= numTiles) break;
+        uint32_t idx[kListItems]; bool have[kListItems];
+#pragma unroll
+        for (int k = 0; k < kListItems; ++k) {
+            const uint32_t e = tile * uint32_t(kListTile) + uint32_t(k) * kListThreads + tid;
+            have[k] = e < v;
+            idx[k] = have[k] ? __ldg(p.visList + e) : 0u;
+        }
+        uint2 ob[kListItems];
+#pragma unroll
+        for (int k = 0; k < kListItems; ++k) ob[k] = have[k] ? __ldg(reinterpret_cast<const uint2*>(p.objs + idx[k])) : make_uint2(p.transformIdBase, 0u);
+        float4 ps[kListItems], qt[kListItems], bs[kListItems];
+#pragma unroll
+        for (int k = 0; k < kListItems; ++k) {
+            const uint32_t t = ob[k].x - p.transformIdBase;
+            ps[k] = have[k] ? __ldg(p.xfPosScale + t) : make_float4(0.f, 0.f, 0.f, 1.f);
+            qt[k] = have[k] ? __ldg(p.xfQuat + t) : make_float4(0.f, 0.f, 0.f, 1.f);
+            bs[k] = have[k] ? __ldg(reinterpret_cast<const float4*>(p.surfaces + ob[k].y)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t lodId[kListItems], rank[kListItems], ballots[kListItems];
+        bool emit[kListItems];
+#pragma unroll
+        for (int k = 0; k < kListItems; ++k) {
+            emit[k] = false; lodId[k] = 0u;
+            if (have[k]) {
+                const Sphere s = view_space_sphere(bs[k].x, bs[k].y, bs[k].z, bs[k].w, ps[k].x, ps[k].y, ps[k].z, ps[k].w, qt[k].x, qt[k].y, qt[k].z, qt[k].w, V);
+                if (frustum_test(s, V)) {
+                    emit[k] = true;
+                    const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p.surfaces + ob[k].y) + 1);         // {materialId, lodOffset, lodCount, vertexOffset}
+                    const uint32_t rel = lod_select(s, ps[k].w, V.lodTarget, hi.y, hi.z, [&](uint32_t li) { return __ldg(&p.lods[li].error); });
+                    lodId[k] = (p.flags & kFlagOnpcLodQuirk) ? rel : rel + hi.y;
+                }
+            }
+            ballots[k] = __ballot_sync(0xFFFFFFFFu, emit[k]);
+            rank[k] = uint32_t(__popc(ballots[k] & laneLt));
+            if (lane == 0) s_cnt[k * WARPS + warp] = uint32_t(__popc(ballots[k]));
+        }
+        __syncthreads();
+        uint32_t total = 0u, offs[kListItems];
+#pragma unroll
+        for (int k = 0; k < kListItems; ++k) {
+            offs[k] = 0u;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) { const uint32_t c = s_cnt[k * WARPS + w]; if (uint32_t(w) < warp) offs[k] += c; }
+        }
+#pragma unroll
+        for (int k = 0; k < kListItems; ++k) {                                   // entries of item 0 precede those of item 1 in the list
+            uint32_t kTotal = 0u;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) kTotal += s_cnt[k * WARPS + w];
+            if (emit[k]) s_desc[total + offs[k] + rank[k]] = make_uint2(idx[k], lodId[k]);
+            total += kTotal;
+        }
+        const uint64_t prefix = lookback_exclusive_prefix_cta<kListThreads>(p.status, tile, total, epoch, s_scratch);   // contains the barrier that publishes s_desc
+        if (tid == 0 && tile == numTiles - 1u) {
+            const uint64_t all = prefix + total;
+            p.counts[0] = uint32_t(all < p.capacity ? all : p.capacity);
+            p.counts[1] = uint32_t(all);
+        }
+        __syncthreads();
+        const uint64_t room = prefix < p.capacity ? p.capacity - prefix : 0ull;
+        const uint32_t nrec = uint32_t(room < total ? room : total);
+        uint2* dst = reinterpret_cast<uint2*>(p.draws + prefix * p.recWords);
+        const uint32_t wpr = p.recWords >> 1;
+        for (uint32_t w = tid; w < nrec * wpr; w += kListThreads) {
+            const uint32_t r = wpr == 3u ? w / 3u : w >> 2, f = w - r * wpr;
+            const uint2 d = s_desc[r];
+            const uint2 L = __ldg(reinterpret_cast<const uint2*>(p.lods + d.y));             // {indexCount, firstIndex}
+            st_cs_u2(dst + w, f == 0u ? make_uint2(p.objectIdBase + d.x, L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
+        }
+    }
+    if (tid == 0) {
+        __threadfence();
+        const uint32_t prev = atomicAdd(&p.ctl->done, 1u);
+        if (prev == gridDim.x - 1u) {
+            uint32_t e = (epoch + 1u) & 0x3FFFFFFFu;
+            p.ctl->epoch = e ? e : 1u;
+            p.ctl->ticket = 0u;
+            p.ctl->done = 0u;
+        }
+    }
+}
+
+cudaError_t launch_early_list(const DrawCullParams& p, int numSMs, cudaStream_t stream)
+{
+    uint32_t maxTiles = p.n == 0 ? 1u : uint32_t((uint64_t(p.n) + kListTile - 1) / kListTile);
+    uint32_t grid = uint32_t(numSMs) * 6u;
+    if (grid > maxTiles) grid = maxTiles;
+    early_list_kernel<<<grid, kListThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_early_sparse(const DrawCullParams& p, cudaStream_t stream)
 {
     if (p.lodCount >= (1u << 20)) return cudaErrorInvalidValue;                   // descriptor packing: 12 bits of index + 20 bits of lod id

@@ -11,7 +11,7 @@ constexpr int kDrawThreads = 512;                    // draw-cull kernels: 16 wa
 constexpr int kDrawDenseWarps = 12;                  // ... 12 of them stream objects (sphere + frustum), 4 evaluate the survivor queue (Hi-Z, LOD)
 constexpr int kDrawItems = 2;
 constexpr int kDrawTile = kDrawDenseWarps * 32 * kDrawItems;   // 768 objects per tile
-constexpr int kCullMinTile = 768;                    // smallest tile any kernel uses: sizes the per-tile status array
+constexpr int kCullMinTile = 512;                    // smallest tile any kernel uses: sizes the per-tile status array
 
 struct DrawCullParams {
     // inputs
@@ -24,6 +24,8 @@ struct DrawCullParams {
     // outputs
     uint32_t* draws;                 // records, recWords u32 each
     uint32_t* counts;                // [0] = written (clamped to capacity), [1] = total
+    uint32_t* visList;               // late pass: ascending LOCAL indices of the objects it found visible (may be null); early-list pass: its input
+    uint32_t* visCount;              // device word holding the length of visList
     // scan state
     ScanCtl* ctl;
     uint64_t* status;
@@ -81,7 +83,8 @@ struct ClusterCullParams {
 
 // launchers (return the cudaError_t of the launch)
 cudaError_t launch_draw_cull(const DrawCullParams& p, int pass, int hiz, int numSMs, cudaStream_t stream);
-cudaError_t launch_early_sparse(const DrawCullParams& p, cudaStream_t stream);   // cull_early.cu: PASS_EARLY for mostly-invisible scenes
+cudaError_t launch_early_sparse(const DrawCullParams& p, cudaStream_t stream);
+cudaError_t launch_early_list(const DrawCullParams& p, int numSMs, cudaStream_t stream);   // cull_early.cu: PASS_EARLY over the late pass's visible list   // cull_early.cu: PASS_EARLY for mostly-invisible scenes
 cudaError_t launch_instance_cull(const InstanceCullParams& p, int numSMs, cudaStream_t stream);
 cudaError_t launch_cluster_expand(const ClusterExpandParams& p, int numSMs, cudaStream_t stream);
 cudaError_t launch_cluster_cull(const ClusterCullParams& p, int hiz, int numSMs, cudaStream_t stream);
