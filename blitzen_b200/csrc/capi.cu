@@ -176,8 +176,9 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.visList = c->visList; p.visCount = c->counts + 4;
     if (pass == PASS_EARLY && c->optEarlyMode == 2 && c->visListValid) CU_TRY(launch_early_list(p, c->numSMs, c->stream));
     else if (pass == PASS_EARLY && c->optEarlyMode >= 1 && p.lodCount < (1u << 20)) CU_TRY(launch_early_sparse(p, c->stream));
+    else if (c->optDrawKernel == 1) CU_TRY(launch_stream_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, int(c->optStreamCfg), c->stream));
     else CU_TRY(launch_draw_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
-    if (pass == PASS_LATE) c->visListValid = true;
+    if (pass == PASS_LATE) c->visListValid = (c->optDrawKernel != 1);
     c->launches++;
     c->lastRecWords = p.recWords;
     return BLZ_OK;
@@ -667,6 +668,8 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (!c || !name) return fail(BLZ_ERR_INVALID, "null argument");
     if (strcmp(name, "pyramid_tma") == 0) { c->optPyramidTma = value; return BLZ_OK; }
     if (strcmp(name, "early_mode") == 0) { c->optEarlyMode = value; return BLZ_OK; }
+    if (strcmp(name, "draw_kernel") == 0) { c->optDrawKernel = value; return BLZ_OK; }
+    if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);
 }
 
