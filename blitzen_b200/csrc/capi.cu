@@ -166,7 +166,7 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.transformIdBase = c->transformIdBase;
     p.surfaceCount = c->nSurf; p.lodCount = c->nLods;
     p.recWords = fmt == BLZ_REC_VK24 ? 6u : 8u;
-    p.flags = flags;
+    p.flags = (flags & kFlagOnpcLodQuirk) | (c->optStreamDynamic ? kFlagDynamicTiles : 0u);
     p.capacity = c->drawCap;
     p.view = make_view_consts(c->view);
     p.pyr = c->pyr;
@@ -176,7 +176,7 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.visList = c->visList; p.visCount = c->counts + 4;
     if (pass == PASS_EARLY && c->optEarlyMode == 2 && c->visListValid) CU_TRY(launch_early_list(p, c->numSMs, c->stream));
     else if (pass == PASS_EARLY && c->optEarlyMode >= 1 && p.lodCount < (1u << 20)) CU_TRY(launch_early_sparse(p, c->stream));
-    else if (c->optDrawKernel == 1) CU_TRY(launch_stream_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, int(c->optStreamCfg), c->stream));
+    else if (c->optDrawKernel == 1) CU_TRY(launch_stream_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, int(c->optStreamCfg), c->numSMs, c->stream));
     else CU_TRY(launch_draw_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
     if (pass == PASS_LATE) c->visListValid = (c->optDrawKernel != 1);
     c->launches++;
@@ -287,7 +287,7 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     for (int i = 0; i < 3; ++i) {
         c->nObjs[i] = counts[i];
         if (counts[i] == 0) continue;
-        TRY_RC(grow(c, c->objs[i], c->capObjs[i], size_t(counts[i]) * sizeof(RenderObject)));
+        TRY_RC(grow(c, c->objs[i], c->capObjs[i], size_t(counts[i]) * sizeof(RenderObject) + 16u));     // + 16: bulk copies of the ragged last tile are rounded up to 16 B
         CU_TRY(cudaMemcpyAsync(c->objs[i], lists[i], size_t(counts[i]) * sizeof(RenderObject), kind, c->stream));
     }
     // transforms: AoS staging -> SoA repack (the per-frame path only reads the two SoA streams)
@@ -320,7 +320,7 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     c->objectIdBase = d->object_id_base; c->transformIdBase = d->transform_id_base;
     // visibility buffer, zero-filled (vulkanRendererSetup.cpp:349)
     const size_t nVis = c->nObjs[0] ? c->nObjs[0] : 1;
-    TRY_RC(grow(c, c->vis, c->capVis, nVis * sizeof(uint32_t)));
+    TRY_RC(grow(c, c->vis, c->capVis, nVis * sizeof(uint32_t) + 16u));
     CU_TRY(cudaMemsetAsync(c->vis, 0, nVis * sizeof(uint32_t), c->stream));
     TRY_RC(grow(c, c->visList, c->capVisList, nVis * sizeof(uint32_t)));
     c->visListValid = false;
@@ -670,6 +670,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (strcmp(name, "early_mode") == 0) { c->optEarlyMode = value; return BLZ_OK; }
     if (strcmp(name, "draw_kernel") == 0) { c->optDrawKernel = value; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
+    if (strcmp(name, "stream_dynamic") == 0) { c->optStreamDynamic = value; return BLZ_OK; }
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);
 }
 
