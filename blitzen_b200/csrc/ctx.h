@@ -45,7 +45,7 @@ struct blz_cull_ctx {
     int64_t optEarlyMode = 2;                 // 0 = pipelined kernel, 1 = sparse (visibility stream) kernel, 2 = visible list when valid, else sparse
     int64_t optDrawKernel = 1;                // 0 = pipelined kernel (cull_draw.cu), 1 = streaming kernel (cull_stream.cu)
     int64_t optStreamDynamic = 1;             // streaming kernel: atomic-ticket tile order (1) or static round-robin (0)
-    int64_t optStreamCfg = 0;                 // CTA shape of the streaming kernel (see launch_pass in cull_stream.cu)
+    int64_t optStreamCfg = 2;                 // CTA shape of the streaming kernel (see launch_pass in cull_stream.cu)
     uint32_t lastRecWords = 6;                // record width (u32 words) of the pass that last wrote `draws`
     // gather (multi-GPU): the presenter owns gatherBuf/gatherFlags; every rank (presenter included) writes through gatherDst*
     uint32_t* gatherBuf = nullptr; uint64_t gatherCap = 0; uint32_t gatherRecWords = 6; uint64_t* gatherFlags = nullptr; bool gatherOwner = false;

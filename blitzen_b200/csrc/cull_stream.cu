@@ -252,10 +252,9 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
         }
 
         uint32_t emitRun = 0u;               // emitters of this warp's span (warp-uniform)
+        uint32_t survMask = 0u, qn = 0u;     // frustum survivors of this thread / of this warp's span
         if (valid) {
             // ---- S1: sphere + frustum planes of tile j, straight-line (inputs in registers) -------------------------------------
-            uint32_t survMask = 0u;
-            uint32_t qn = 0u;
             {
                 Sphere sph[ITEMS];
 #pragma unroll
@@ -278,36 +277,13 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
                     qn += uint32_t(__popc(ball));
                 }
             }
-            __syncwarp();
-            // ---- S2: the warp evaluates its own survivors, 32 at a time: Hi-Z + LOD; emitters are compacted in place -----------------
-            for (uint32_t e0 = 0u; e0 < qn; e0 += 32u) {
-                const uint32_t e = e0 + lane;
-                uint32_t res = 0u, local = 0u;
-                if (e < qn) {
-                    const uint2 m = qMeta[e];
-                    local = m.y & 0xFFFFu;
-                    res = eval_entry<PASS, HIZ>(qSphere[e], m, qSurf[e], surfT, lodT, p);
-                    if (PASS == PASS_LATE) sVis[local - warp * uint32_t(WSPAN)] = res & 1u;
-                }
-                const uint32_t eb = __ballot_sync(0xFFFFFFFFu, (res & 2u) != 0u);
-                __syncwarp();                                      // every qSurf[e] of this round is read before wDesc (same words, lower or equal index) is written
-                if (res & 2u) wDesc[emitRun + uint32_t(__popc(eb & laneLt))] = local | ((res >> 2) << kSLocalBits);
-                emitRun += uint32_t(__popc(eb));
-            }
-            if (lane == 0) s_warpCnt[ju & 1u][warp] = emitRun;
-            if (PASS == PASS_LATE) {
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k)                    // LateDrawCull.comp.glsl:70, coalesced
-                    if ((inMask >> k) & 1u) p.visibility[tileBase + localBase + uint32_t(k) * 32u] = ((survMask >> k) & 1u) ? sVis[lane + uint32_t(k) * 32u] : 0u;
-            }
         }
-
+        const uint32_t inMaskJ = inMask;
         if (dyn && tid == 0) {       // the ticket is back by now; its ring stage (that of tile j) was consumed before the barrier of iteration j-1
             s_tiles[(mm + 1u) & 7u] = ticket;
             if (ticket < p.numTiles) issue_tile(ticket, (mm + 1u) % uint32_t(D));
         }
-        // ---- S3: fetch tile j+1: its RenderObject / visibility words are in the ring; the transform gather goes out now and is
+        // ---- S2: fetch tile j+1: its RenderObject / visibility words are in the ring; the transform gather goes out now and is
         //      consumed at the top of the next iteration ------------------------------------------------------------------------
         const uint32_t nextTile = tile_of(mm);
         if (nextTile != kNoTile) {
@@ -333,6 +309,32 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
                 inMask |= (in ? 1u : 0u) << k; actMask |= (act ? 1u : 0u) << k; vpMask |= (vprev ? 1u : 0u) << k;
             }
         }
+        if (valid) {
+            __syncwarp();
+            // ---- S3: the warp evaluates its own survivors, 32 at a time: Hi-Z + LOD; emitters are compacted in place -----------------
+            for (uint32_t e0 = 0u; e0 < qn; e0 += 32u) {
+                const uint32_t e = e0 + lane;
+                uint32_t res = 0u, local = 0u;
+                if (e < qn) {
+                    const uint2 m = qMeta[e];
+                    local = m.y & 0xFFFFu;
+                    res = eval_entry<PASS, HIZ>(qSphere[e], m, qSurf[e], surfT, lodT, p);
+                    if (PASS == PASS_LATE) sVis[local - warp * uint32_t(WSPAN)] = res & 1u;
+                }
+                const uint32_t eb = __ballot_sync(0xFFFFFFFFu, (res & 2u) != 0u);
+                __syncwarp();                                      // every qSurf[e] of this round is read before wDesc (same words, lower or equal index) is written
+                if (res & 2u) wDesc[emitRun + uint32_t(__popc(eb & laneLt))] = local | ((res >> 2) << kSLocalBits);
+                emitRun += uint32_t(__popc(eb));
+            }
+            if (lane == 0) s_warpCnt[ju & 1u][warp] = emitRun;
+            if (PASS == PASS_LATE) {
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k)                    // LateDrawCull.comp.glsl:70, coalesced
+                    if ((inMaskJ >> k) & 1u) p.visibility[tileBase + localBase + uint32_t(k) * 32u] = ((survMask >> k) & 1u) ? sVis[lane + uint32_t(k) * 32u] : 0u;
+            }
+        }
+
         if (prev2 != kNoTile) {
             uint32_t part = 0u;
 #pragma unroll
@@ -460,6 +462,9 @@ cudaError_t launch_pass(const DrawCullParams& p, int cfg, int numSMs, cudaStream
     case 3: return launch_cfg<PASS, HIZ, 512, 2, 3>(p, numSMs, stream);
     case 4: return launch_cfg<PASS, HIZ, 128, 4, 6>(p, numSMs, stream);
     case 5: return launch_cfg<PASS, HIZ, 512, 2, 2>(p, numSMs, stream);
+    case 6: return launch_cfg<PASS, HIZ, 256, 3, 4>(p, numSMs, stream);
+    case 7: return launch_cfg<PASS, HIZ, 512, 3, 2>(p, numSMs, stream);
+    case 8: return launch_cfg<PASS, HIZ, 128, 4, 7>(p, numSMs, stream);
     default: return launch_cfg<PASS, HIZ, 256, 2, 6>(p, numSMs, stream);
     }
 }
