@@ -292,7 +292,7 @@ def main():
     b_early, b_late = algorithmic_bytes(n, vis_prev, early_total, late_total)
     b_pyr = pyramid_bytes(DEPTH_W, DEPTH_H, pyr_texels)
     late_gbs = b_late / (t_late * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "draw_cull_kernel<PASS_LATE> (late pass: frustum + Hi-Z + LOD + compaction + visibility write)",
+    roofline = {"bound": "hbm", "kernel": "stream_cull_kernel<PASS_LATE> (late pass: frustum + Hi-Z + LOD + compaction + visibility write)",
                 "achieved": late_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": late_gbs / peak,
                 "algorithmic_bytes_per_launch": b_late, "bytes_per_object": 48, "objects_per_launch": n, "launch_ms": t_late,
                 "traffic": None,

@@ -170,15 +170,26 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.capacity = c->drawCap;
     p.view = make_view_consts(c->view);
     p.pyr = c->pyr;
-    // The late pass leaves the ascending list of the ids it marked visible; as long as nothing else writes visibility[] the next
-    // early pass culls that list instead of streaming over all N objects.  Otherwise: the sparse kernel (4-B visibility stream +
-    // gather for the visible ones).  option early_mode: 0 = pipelined kernel, 1 = sparse kernel, 2 = list when valid (default).
+    // Early pass, option early_mode: 3 = pipelined visibility-stream kernel (default), 2 = the late pass's visible-id list when valid
+    // (pipelined draw kernel only), 1 = one-shot sparse kernel, 0 = the generic draw kernel.
     p.visList = c->visList; p.visCount = c->counts + 4;
-    if (pass == PASS_EARLY && c->optEarlyMode == 2 && c->visListValid) CU_TRY(launch_early_list(p, c->numSMs, c->stream));
+    const bool stream = c->optDrawKernel == 1;
+    p.visBits = nullptr;
+    if (pass == PASS_LATE && stream) p.visBits = c->visBits;                      // the streaming late pass keeps the bit mask in step
+    if (pass == PASS_EARLY && c->optEarlyMode == 3 && c->optEarlyBits && p.lodCount < (1u << 20)) {
+        if (!c->visBitsValid) {                                                      // something else wrote visibility[]: rebuild the mask (one 4 B/object pass)
+            CU_TRY(launch_pack_vis_bits(c->vis, c->visBits, p.n, c->stream));
+            c->launches++;
+            c->visBitsValid = true;
+        }
+        p.visBits = c->visBits;
+    }
+    if (pass == PASS_EARLY && c->optEarlyMode == 3 && p.lodCount < (1u << 20)) CU_TRY(launch_early_stream(p, c->numSMs, c->stream));
+    else if (pass == PASS_EARLY && c->optEarlyMode == 2 && c->visListValid) CU_TRY(launch_early_list(p, c->numSMs, c->stream));
     else if (pass == PASS_EARLY && c->optEarlyMode >= 1 && p.lodCount < (1u << 20)) CU_TRY(launch_early_sparse(p, c->stream));
-    else if (c->optDrawKernel == 1) CU_TRY(launch_stream_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, int(c->optStreamCfg), c->numSMs, c->stream));
+    else if (stream) CU_TRY(launch_stream_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, int(c->optStreamCfg), c->numSMs, c->stream));
     else CU_TRY(launch_draw_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
-    if (pass == PASS_LATE) c->visListValid = (c->optDrawKernel != 1);
+    if (pass == PASS_LATE) { c->visListValid = !stream; c->visBitsValid = stream; }
     c->launches++;
     c->lastRecWords = p.recWords;
     return BLZ_OK;
@@ -226,8 +237,8 @@ static void free_scene(blz_cull_ctx* c)
     for (int i = 0; i < 3; ++i) { dfree(c->objs[i]); c->nObjs[i] = 0; }
     dfree(c->xfPS); dfree(c->xfQ); dfree(c->xfStage); c->nXf = 0; c->xfStageCap = 0;
     dfree(c->surf); dfree(c->lods); dfree(c->clusters); dfree(c->lodInst); dfree(c->bucketCap);
-    dfree(c->vis); dfree(c->visList); dfree(c->draws); dfree(c->dispatch); dfree(c->instIdx);
-    c->capVisList = 0; c->visListValid = false;
+    dfree(c->vis); dfree(c->visList); dfree(c->visBits); dfree(c->draws); dfree(c->dispatch); dfree(c->instIdx);
+    c->capVisList = 0; c->visListValid = false; c->capVisBits = 0; c->visBitsValid = false;
     c->nSurf = c->nLods = c->nClusters = c->nLodInst = 0; c->drawCap = c->dispatchCap = c->instCap = 0;
     c->capObjs[0] = c->capObjs[1] = c->capObjs[2] = 0;
     c->capXfPS = c->capXfQ = c->capSurf = c->capLods = c->capClusters = c->capLodInst = c->capBucket = 0;
@@ -324,6 +335,10 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     CU_TRY(cudaMemsetAsync(c->vis, 0, nVis * sizeof(uint32_t), c->stream));
     TRY_RC(grow(c, c->visList, c->capVisList, nVis * sizeof(uint32_t)));
     c->visListValid = false;
+    const size_t bitBytes = ((nVis + 4095) / 4096) * 512 + 512;                        // whole 4096-object tiles of the bit-mask early pass
+    TRY_RC(grow(c, c->visBits, c->capVisBits, bitBytes));
+    CU_TRY(cudaMemsetAsync(c->visBits, 0, c->capVisBits, c->stream));
+    c->visBitsValid = true;
     // draw buffer (sized for the wider DX32 record), cluster dispatch buffer
     c->drawCap = d->draw_capacity ? d->draw_capacity : (maxList ? maxList : 1);
     TRY_RC(grow(c, c->draws, c->capDraws, size_t(c->drawCap) * 8u * sizeof(uint32_t)));
@@ -396,7 +411,8 @@ int blz_cull_reset_visibility(blz_cull_ctx* c)
     if (!c || !c->vis) return fail(BLZ_ERR_INVALID, "no scene uploaded");
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMemsetAsync(c->vis, 0, size_t(c->nObjs[0] ? c->nObjs[0] : 1) * sizeof(uint32_t), c->stream));
-    c->visListValid = false;
+    CU_TRY(cudaMemsetAsync(c->visBits, 0, c->capVisBits, c->stream));
+    c->visListValid = false; c->visBitsValid = true;
     return BLZ_OK;
 }
 
@@ -406,7 +422,7 @@ int blz_cull_write_visibility(blz_cull_ctx* c, const uint32_t* host)
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMemcpyAsync(c->vis, host, size_t(c->nObjs[0]) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
-    c->visListValid = false;
+    c->visListValid = false; c->visBitsValid = false;
     return BLZ_OK;
 }
 
@@ -668,6 +684,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (!c || !name) return fail(BLZ_ERR_INVALID, "null argument");
     if (strcmp(name, "pyramid_tma") == 0) { c->optPyramidTma = value; return BLZ_OK; }
     if (strcmp(name, "early_mode") == 0) { c->optEarlyMode = value; return BLZ_OK; }
+    if (strcmp(name, "early_bits") == 0) { c->optEarlyBits = value; return BLZ_OK; }
     if (strcmp(name, "draw_kernel") == 0) { c->optDrawKernel = value; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     if (strcmp(name, "stream_dynamic") == 0) { c->optStreamDynamic = value; return BLZ_OK; }

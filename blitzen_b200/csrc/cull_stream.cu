@@ -330,8 +330,13 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
             if (PASS == PASS_LATE) {
                 __syncwarp();
 #pragma unroll
-                for (int k = 0; k < ITEMS; ++k)                    // LateDrawCull.comp.glsl:70, coalesced
-                    if ((inMaskJ >> k) & 1u) p.visibility[tileBase + localBase + uint32_t(k) * 32u] = ((survMask >> k) & 1u) ? sVis[lane + uint32_t(k) * 32u] : 0u;
+                for (int k = 0; k < ITEMS; ++k) {                  // LateDrawCull.comp.glsl:70, coalesced
+                    const uint32_t v = ((survMask >> k) & 1u) ? sVis[lane + uint32_t(k) * 32u] : 0u;
+                    if ((inMaskJ >> k) & 1u) p.visibility[tileBase + localBase + uint32_t(k) * 32u] = v;
+                    // the same flags as a bit mask (one word per 32 consecutive objects): what the next early pass streams
+                    const uint32_t vb = __ballot_sync(0xFFFFFFFFu, v != 0u);
+                    if (p.visBits != nullptr && lane == 0 && ((inMaskJ >> k) & 1u)) p.visBits[(tileBase + localBase + uint32_t(k) * 32u) >> 5] = vb;
+                }
             }
         }
 
