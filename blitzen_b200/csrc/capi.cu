@@ -136,6 +136,25 @@ int grow(blz_cull_ctx* c, T*& p, size_t& capBytes, size_t needBytes)
 }
 #define TRY_RC(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
 
+// Visibility state has two forms: the reference's u32 per object (c->vis) and 1 bit per object (c->visBits), which is what the
+// streaming late pass and the pipelined early pass read and write.  Each is converted from the other on demand.
+int ensure_vis_bits(blz_cull_ctx* c)
+{
+    if (c->visBitsValid) return BLZ_OK;
+    CU_TRY(launch_pack_vis_bits(c->vis, c->visBits, c->nObjs[0], c->stream));
+    c->launches++;
+    c->visBitsValid = true;
+    return BLZ_OK;
+}
+int ensure_vis_words(blz_cull_ctx* c)
+{
+    if (c->visWordsValid) return BLZ_OK;
+    CU_TRY(launch_unpack_vis_bits(c->visBits, c->vis, c->nObjs[0], c->stream));
+    c->launches++;
+    c->visWordsValid = true;
+    return BLZ_OK;
+}
+
 int check_list(blz_cull_ctx* c, int list)
 {
     if (list < 0 || list > 2) return fail(BLZ_ERR_INVALID, "list %d out of range", list);
@@ -174,22 +193,23 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     // (pipelined draw kernel only), 1 = one-shot sparse kernel, 0 = the generic draw kernel.
     p.visList = c->visList; p.visCount = c->counts + 4;
     const bool stream = c->optDrawKernel == 1;
+    const bool earlyStream = pass == PASS_EARLY && c->optEarlyMode == 3 && p.lodCount < (1u << 20);
+    const bool usesBits = (pass == PASS_LATE && stream) || (earlyStream && c->optEarlyBits);
+    const bool usesWords = (pass == PASS_EARLY || pass == PASS_LATE) && !usesBits;
     p.visBits = nullptr;
-    if (pass == PASS_LATE && stream) p.visBits = c->visBits;                      // the streaming late pass keeps the bit mask in step
-    if (pass == PASS_EARLY && c->optEarlyMode == 3 && c->optEarlyBits && p.lodCount < (1u << 20)) {
-        if (!c->visBitsValid) {                                                      // something else wrote visibility[]: rebuild the mask (one 4 B/object pass)
-            CU_TRY(launch_pack_vis_bits(c->vis, c->visBits, p.n, c->stream));
-            c->launches++;
-            c->visBitsValid = true;
-        }
-        p.visBits = c->visBits;
-    }
-    if (pass == PASS_EARLY && c->optEarlyMode == 3 && p.lodCount < (1u << 20)) CU_TRY(launch_early_stream(p, c->numSMs, c->stream));
+    if (usesBits) { TRY_RC(ensure_vis_bits(c)); p.visBits = c->visBits; }
+    if (usesWords) TRY_RC(ensure_vis_words(c));
+    if (pass == PASS_LATE && stream && !c->optVisWords) p.visibility = nullptr;    // the mask is the state; the u32 form is materialised on demand
+    if (earlyStream) CU_TRY(launch_early_stream(p, c->numSMs, c->stream));
     else if (pass == PASS_EARLY && c->optEarlyMode == 2 && c->visListValid) CU_TRY(launch_early_list(p, c->numSMs, c->stream));
     else if (pass == PASS_EARLY && c->optEarlyMode >= 1 && p.lodCount < (1u << 20)) CU_TRY(launch_early_sparse(p, c->stream));
     else if (stream) CU_TRY(launch_stream_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, int(c->optStreamCfg), c->numSMs, c->stream));
     else CU_TRY(launch_draw_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
-    if (pass == PASS_LATE) { c->visListValid = !stream; c->visBitsValid = stream; }
+    if (pass == PASS_LATE) {
+        c->visListValid = !stream;
+        c->visBitsValid = stream;
+        c->visWordsValid = !stream || c->optVisWords != 0;
+    }
     c->launches++;
     c->lastRecWords = p.recWords;
     return BLZ_OK;
@@ -338,7 +358,7 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     const size_t bitBytes = ((nVis + 4095) / 4096) * 512 + 512;                        // whole 4096-object tiles of the bit-mask early pass
     TRY_RC(grow(c, c->visBits, c->capVisBits, bitBytes));
     CU_TRY(cudaMemsetAsync(c->visBits, 0, c->capVisBits, c->stream));
-    c->visBitsValid = true;
+    c->visBitsValid = true; c->visWordsValid = true;
     // draw buffer (sized for the wider DX32 record), cluster dispatch buffer
     c->drawCap = d->draw_capacity ? d->draw_capacity : (maxList ? maxList : 1);
     TRY_RC(grow(c, c->draws, c->capDraws, size_t(c->drawCap) * 8u * sizeof(uint32_t)));
@@ -412,7 +432,7 @@ int blz_cull_reset_visibility(blz_cull_ctx* c)
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMemsetAsync(c->vis, 0, size_t(c->nObjs[0] ? c->nObjs[0] : 1) * sizeof(uint32_t), c->stream));
     CU_TRY(cudaMemsetAsync(c->visBits, 0, c->capVisBits, c->stream));
-    c->visListValid = false; c->visBitsValid = true;
+    c->visListValid = false; c->visBitsValid = true; c->visWordsValid = true;
     return BLZ_OK;
 }
 
@@ -422,7 +442,7 @@ int blz_cull_write_visibility(blz_cull_ctx* c, const uint32_t* host)
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMemcpyAsync(c->vis, host, size_t(c->nObjs[0]) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
-    c->visListValid = false; c->visBitsValid = false;
+    c->visListValid = false; c->visBitsValid = false; c->visWordsValid = true;
     return BLZ_OK;
 }
 
@@ -582,6 +602,7 @@ int blz_cull_get_outputs(blz_cull_ctx* c, blz_outputs* o)
 {
     if (!c || !o) return fail(BLZ_ERR_INVALID, "null argument");
     memset(o, 0, sizeof(*o));
+    if (c->vis && c->nObjs[0]) TRY_RC(ensure_vis_words(c));                  // the u32 view is materialised on demand (stream-ordered)
     o->draws = c->draws; o->draw_count = c->counts; o->visibility = c->vis;
     o->cluster_dispatch = c->dispatch; o->cluster_count = c->counts ? c->counts + 2 : nullptr;
     o->instance_indices = c->instIdx; o->instance_counts = reinterpret_cast<uint32_t*>(c->lodInst);
@@ -632,6 +653,7 @@ int blz_cull_read_visibility(blz_cull_ctx* c, uint32_t* host)
 {
     if (!c || !c->vis || !host) return fail(BLZ_ERR_INVALID, "no scene uploaded / null pointer");
     CU_TRY(cudaSetDevice(c->device));
+    TRY_RC(ensure_vis_words(c));
     if (c->nObjs[0]) CU_TRY(cudaMemcpyAsync(host, c->vis, size_t(c->nObjs[0]) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     return BLZ_OK;
@@ -685,6 +707,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (strcmp(name, "pyramid_tma") == 0) { c->optPyramidTma = value; return BLZ_OK; }
     if (strcmp(name, "early_mode") == 0) { c->optEarlyMode = value; return BLZ_OK; }
     if (strcmp(name, "early_bits") == 0) { c->optEarlyBits = value; return BLZ_OK; }
+    if (strcmp(name, "vis_words") == 0) { c->optVisWords = value; return BLZ_OK; }
     if (strcmp(name, "draw_kernel") == 0) { c->optDrawKernel = value; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     if (strcmp(name, "stream_dynamic") == 0) { c->optStreamDynamic = value; return BLZ_OK; }

@@ -27,7 +27,8 @@ struct blz_cull_ctx {
     uint32_t* counts = nullptr;               // [0..1] draws, [2..3] cluster dispatch, [4] length of visList
     uint32_t* visList = nullptr; size_t capVisList = 0;   // ascending ids the last late pass found visible
     uint32_t* visBits = nullptr; size_t capVisBits = 0;   // 1 bit per object, padded to whole early-pass tiles
-    bool visBitsValid = false;                // visBits mirrors visibility[]
+    bool visBitsValid = false;                // visBits is current
+    bool visWordsValid = false;               // vis (u32 per object, the reference's form) is current; at least one of the two always is
     bool visListValid = false;                // true while visibility[] has not been written by anything but that late pass
     uint32_t* dispatch = nullptr; uint64_t dispatchCap = 0;
     uint32_t* instIdx = nullptr; uint64_t instCap = 0;
@@ -46,6 +47,7 @@ struct blz_cull_ctx {
     int64_t optPyramidTma = 1;
     int64_t optEarlyMode = 3;                 // 3 = pipelined visibility-stream kernel, 2 = visible list when valid else sparse, 1 = one-shot sparse kernel, 0 = generic draw kernel
     int64_t optEarlyBits = 1;                 // pipelined early pass streams the 1-bit mask (1) or the 4-B visibility words (0)
+    int64_t optVisWords = 0;                  // 1: the streaming late pass also writes the u32-per-object visibility buffer every frame (else on demand)
     int64_t optDrawKernel = 1;                // 0 = pipelined kernel (cull_draw.cu), 1 = streaming kernel (cull_stream.cu)
     int64_t optStreamDynamic = 1;             // streaming kernel: atomic-ticket tile order (1) or static round-robin (0)
     int64_t optStreamCfg = 2;                 // CTA shape of the streaming kernel (see launch_pass in cull_stream.cu)

@@ -647,6 +647,20 @@ __global__ void pack_vis_bits_kernel(const uint32_t* __restrict__ vis, uint32_t*
     if ((threadIdx.x & 31u) == 0u && (i >> 5) < words) bits[i >> 5] = b;
 }
 
+// 1 bit per object -> the reference's u32-per-object visibility buffer
+__global__ void unpack_vis_bits_kernel(const uint32_t* __restrict__ bits, uint32_t* __restrict__ vis, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vis[i] = (__ldg(bits + (i >> 5)) >> (i & 31u)) & 1u;
+}
+
+cudaError_t launch_unpack_vis_bits(const uint32_t* bits, uint32_t* vis, uint32_t n, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    unpack_vis_bits_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(bits, vis, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_pack_vis_bits(const uint32_t* vis, uint32_t* bits, uint32_t n, cudaStream_t stream)
 {
     const uint32_t words = (n + 31u) / 32u;

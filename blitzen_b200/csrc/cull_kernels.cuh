@@ -87,6 +87,7 @@ cudaError_t launch_draw_cull(const DrawCullParams& p, int pass, int hiz, int num
 cudaError_t launch_stream_cull(const DrawCullParams& p, int pass, int hiz, int cfg, int numSMs, cudaStream_t stream);   // cull_stream.cu
 cudaError_t launch_early_stream(const DrawCullParams& p, int numSMs, cudaStream_t stream);   // cull_early.cu: pipelined early pass (default)
 cudaError_t launch_pack_vis_bits(const uint32_t* vis, uint32_t* bits, uint32_t n, cudaStream_t stream);   // cull_early.cu
+cudaError_t launch_unpack_vis_bits(const uint32_t* bits, uint32_t* vis, uint32_t n, cudaStream_t stream); // cull_early.cu
 cudaError_t launch_early_sparse(const DrawCullParams& p, cudaStream_t stream);
 cudaError_t launch_early_list(const DrawCullParams& p, int numSMs, cudaStream_t stream);   // cull_early.cu: PASS_EARLY over the late pass's visible list   // cull_early.cu: PASS_EARLY for mostly-invisible scenes
 cudaError_t launch_instance_cull(const InstanceCullParams& p, int numSMs, cudaStream_t stream);

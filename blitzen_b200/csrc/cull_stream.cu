@@ -135,8 +135,11 @@ template <int PASS, int HIZ, int THREADS, int ITEMS, int MINB, bool SMEM_TABLES>
 __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid_constant__ DrawCullParams p)
 {
     constexpr int TILE = THREADS * ITEMS, WARPS = THREADS / 32, D = kStreamDepth, WSPAN = 32 * ITEMS;   // WSPAN: objects of a tile owned by one warp
-    constexpr bool HAS_VIS = (PASS == PASS_EARLY || PASS == PASS_LATE);
+    constexpr bool VIS_WORDS = (PASS == PASS_EARLY);     // last frame's visibility arrives as 4-B words (generic early pass) ...
+    constexpr bool VIS_BITS = (PASS == PASS_LATE);       // ... or as the 1-bit-per-object mask (late pass): 128 B per tile instead of 4 KB
+    constexpr int VIS_STAGE_WORDS = VIS_WORDS ? TILE : (VIS_BITS ? TILE / 32 : 0);
     static_assert(TILE <= (1 << kSLocalBits), "descriptor packing");
+    static_assert(!VIS_BITS || (TILE / 32 * 4) % 16 == 0, "bulk copy granularity of the mask words");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar[D];
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
     // ---- carve shared memory --------------------------------------------------------------------------------------------------
     unsigned char* sp = smem_raw;
     uint2* objRing = reinterpret_cast<uint2*>(sp);       sp += size_t(D) * TILE * sizeof(uint2);      // TMA destination: RenderObject stream
-    uint32_t* visRing = reinterpret_cast<uint32_t*>(sp); sp += HAS_VIS ? size_t(D) * TILE * sizeof(uint32_t) : 0;   // TMA destination: visibility stream
+    uint32_t* visRing = reinterpret_cast<uint32_t*>(sp); sp += size_t(D) * VIS_STAGE_WORDS * sizeof(uint32_t);     // TMA destination: visibility stream (words or mask)
     // per-warp private survivor queue (WSPAN entries each): view-space sphere, {scale bits, index in tile | visPrev << 16}, surfaceId
     float4* qSphere = reinterpret_cast<float4*>(sp) + warp * WSPAN;     sp += size_t(TILE) * sizeof(float4);
     uint2* qMeta = reinterpret_cast<uint2*>(sp) + warp * WSPAN;         sp += size_t(TILE) * sizeof(uint2);
@@ -181,10 +184,12 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
     auto issue_tile = [&](uint32_t t, uint32_t stage) {
         const uint32_t first = t * uint32_t(TILE);
         const uint32_t cnt = min(uint32_t(TILE), p.n - first);
-        const uint32_t ob = (cnt * 8u + 15u) & ~15u, vb = HAS_VIS ? ((cnt * 4u + 15u) & ~15u) : 0u;     // buffers are padded by 16 B (capi.cu)
+        const uint32_t ob = (cnt * 8u + 15u) & ~15u;                                                       // buffers are padded by 16 B (capi.cu)
+        const uint32_t vb = VIS_WORDS ? ((cnt * 4u + 15u) & ~15u) : (VIS_BITS ? uint32_t(TILE / 32 * 4) : 0u);   // the mask is padded to whole tiles
         mbar_expect_tx(&s_bar[stage], ob + vb);
         tma_load_1d(objRing + stage * TILE, p.objs + first, ob, &s_bar[stage]);
-        if (HAS_VIS) tma_load_1d(visRing + stage * TILE, p.visibility + first, vb, &s_bar[stage]);
+        if (VIS_WORDS) tma_load_1d(visRing + stage * VIS_STAGE_WORDS, p.visibility + first, vb, &s_bar[stage]);
+        if (VIS_BITS) tma_load_1d(visRing + stage * VIS_STAGE_WORDS, p.visBits + (first >> 5), vb, &s_bar[stage]);
     };
 
     // Tile order.  STATIC: the CTA's m-th tile is m * gridDim.x + blockIdx.x (all CTAs co-resident: the grid is sized by the
@@ -290,14 +295,14 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
             const uint32_t stage = mm % uint32_t(D);
             mbar_wait(&s_bar[stage], (mm / uint32_t(D)) & 1u);
             const uint2* ob = objRing + stage * TILE + localBase;
-            const uint32_t* vr = visRing + stage * TILE + localBase;
+            const uint32_t* vr = visRing + stage * VIS_STAGE_WORDS + (VIS_WORDS ? localBase : warp * uint32_t(ITEMS));
             const uint32_t left = p.n - nextTile * uint32_t(TILE);         // objects from the tile's first to the end of the list (>= 1)
             actMask = 0u; inMask = 0u; vpMask = 0u;
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
                 const bool in = localBase + uint32_t(k) * 32u < left;
                 const uint2 o = ob[k * 32];
-                const uint32_t v = HAS_VIS ? vr[k * 32] : 0u;
+                const uint32_t v = VIS_WORDS ? vr[k * 32] : (VIS_BITS ? ((vr[k] >> lane) & 1u) : 0u);
                 const bool vprev = in && v != 0u;
                 const bool act = (PASS == PASS_EARLY) ? vprev : in;                        // InitialDrawCull.comp.glsl:21-24
                 sid[k] = in ? o.y : 0u;                                                    // the ragged tail of the ring holds stale words
@@ -332,10 +337,11 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
 #pragma unroll
                 for (int k = 0; k < ITEMS; ++k) {                  // LateDrawCull.comp.glsl:70, coalesced
                     const uint32_t v = ((survMask >> k) & 1u) ? sVis[lane + uint32_t(k) * 32u] : 0u;
-                    if ((inMaskJ >> k) & 1u) p.visibility[tileBase + localBase + uint32_t(k) * 32u] = v;
-                    // the same flags as a bit mask (one word per 32 consecutive objects): what the next early pass streams
+                    // visibility lives as a bit mask (one word per 32 consecutive objects): what the next early and late passes stream;
+                    // the reference's u32-per-object form is written too when the caller asked for it (option vis_words)
+                    if (p.visibility != nullptr && ((inMaskJ >> k) & 1u)) p.visibility[tileBase + localBase + uint32_t(k) * 32u] = v;
                     const uint32_t vb = __ballot_sync(0xFFFFFFFFu, v != 0u);
-                    if (p.visBits != nullptr && lane == 0 && ((inMaskJ >> k) & 1u)) p.visBits[(tileBase + localBase + uint32_t(k) * 32u) >> 5] = vb;
+                    if (lane == 0 && ((inMaskJ >> k) & 1u)) p.visBits[(tileBase + localBase + uint32_t(k) * 32u) >> 5] = vb;
                 }
             }
         }
@@ -437,11 +443,11 @@ template <int PASS, int HIZ, int THREADS, int ITEMS, int MINB>
 cudaError_t launch_cfg(const DrawCullParams& p, int numSMs, cudaStream_t stream)
 {
     constexpr int TILE = THREADS * ITEMS;
-    constexpr bool HAS_VIS = (PASS == PASS_EARLY || PASS == PASS_LATE);
+    constexpr size_t VIS_STAGE_BYTES = (PASS == PASS_EARLY) ? size_t(TILE) * 4 : ((PASS == PASS_LATE) ? size_t(TILE) / 8 : 0);
     if (p.lodCount >= (1u << (30 - kSLocalBits))) return cudaErrorInvalidValue;     // descriptor packing (checked by the C-ABI layer too)
     const size_t tableBytes = (size_t(p.surfaceCount) + p.lodCount) * 32u;
     const bool smemTables = tableBytes <= 8192u;
-    const size_t smem = (smemTables ? tableBytes : 0u) + size_t(TILE) * (size_t(kStreamDepth) * (8 + (HAS_VIS ? 4 : 0)) + 16 + 8 + 4 + (PASS == PASS_LATE ? 4 : 0) + 4 * kStagesS);
+    const size_t smem = (smemTables ? tableBytes : 0u) + size_t(kStreamDepth) * VIS_STAGE_BYTES + size_t(TILE) * (size_t(kStreamDepth) * 8 + 16 + 8 + 4 + (PASS == PASS_LATE ? 4 : 0) + 4 * kStagesS);
     auto kernel = smemTables ? stream_cull_kernel<PASS, HIZ, THREADS, ITEMS, MINB, true> : stream_cull_kernel<PASS, HIZ, THREADS, ITEMS, MINB, false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
