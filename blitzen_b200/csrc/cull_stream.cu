@@ -67,7 +67,7 @@ constexpr uint32_t kSLocalMask = (1u << kSLocalBits) - 1u;
 // Evaluates queue entry e of a warp's private queue: Hi-Z (late / temporal passes) and LOD selection for emitters.
 // Returns visible | emit << 1 | lodId << 2.
 template <int PASS, int HIZ>
-__device__ __forceinline__ uint32_t eval_entry(const float4 q, const uint2 m, const uint32_t sidx,
+__device__ __forceinline__ uint32_t eval_entry(const float4 q, const uint2 m /* {scale bits, index in tile | visPrev << 16} */, const uint32_t sidx,
                                                const PrimitiveSurface* surfT, const LodData* lodT, const DrawCullParams& p)
 {
     constexpr bool HAS_HIZ = (PASS == PASS_LATE || PASS == PASS_TEMPORAL);
@@ -160,13 +160,11 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
     unsigned char* sp = smem_raw;
     uint2* objRing = reinterpret_cast<uint2*>(sp);       sp += size_t(D) * TILE * sizeof(uint2);      // TMA destination: RenderObject stream
     uint32_t* visRing = reinterpret_cast<uint32_t*>(sp); sp += size_t(D) * VIS_STAGE_WORDS * sizeof(uint32_t);     // TMA destination: visibility stream (words or mask)
-    // per-warp private survivor queue (WSPAN entries each): view-space sphere, {scale bits, index in tile | visPrev << 16}, surfaceId
-    float4* qSphere = reinterpret_cast<float4*>(sp) + warp * WSPAN;     sp += size_t(TILE) * sizeof(float4);
-    uint2* qMeta = reinterpret_cast<uint2*>(sp) + warp * WSPAN;         sp += size_t(TILE) * sizeof(uint2);
-    uint32_t* qSurf = reinterpret_cast<uint32_t*>(sp) + warp * WSPAN;   sp += size_t(TILE) * sizeof(uint32_t);
-    uint32_t* sVis = reinterpret_cast<uint32_t*>(sp) + warp * WSPAN;    sp += (PASS == PASS_LATE) ? size_t(TILE) * sizeof(uint32_t) : 0;   // new visibility per object of the span
+    // per-warp private survivor queue, WSPAN entries of 32 B: {view-space sphere} {scale bits, index in tile | visPrev << 16, surfaceId, D}
+    // where D of entry i is the i-th EMITTER descriptor of the span (a compact list threaded through the entries' last words: it is
+    // written by the evaluation of entry e >= i and nothing else reads that word)
+    uint4* queue = reinterpret_cast<uint4*>(sp) + warp * (WSPAN * 2);   sp += size_t(TILE) * 32;
     uint32_t* stageB = reinterpret_cast<uint32_t*>(sp);  sp += size_t(kStagesS) * TILE * sizeof(uint32_t);   // survivor descriptors of whole tiles
-    uint32_t* wDesc = qSurf;                                                                          // the warp's emitters, compact (aliases qSurf: see below)
     const PrimitiveSurface* surfT = p.surfaces;
     const LodData* lodT = p.lods;
     if (SMEM_TABLES) {
@@ -274,10 +272,9 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
                 for (int k = 0; k < ITEMS; ++k) {
                     const uint32_t ball = __ballot_sync(0xFFFFFFFFu, (survMask >> k) & 1u);
                     if ((survMask >> k) & 1u) {
-                        const uint32_t slot = qn + uint32_t(__popc(ball & laneLt));
-                        qSphere[slot] = make_float4(sph[k].x, sph[k].y, sph[k].z, sph[k].r);
-                        qMeta[slot] = make_uint2(__float_as_uint(ps[k].w), (localBase + uint32_t(k) * 32u) | (((vpMask >> k) & 1u) << 16));
-                        qSurf[slot] = sid[k];
+                        uint4* e = queue + 2u * (qn + uint32_t(__popc(ball & laneLt)));
+                        e[0] = make_uint4(__float_as_uint(sph[k].x), __float_as_uint(sph[k].y), __float_as_uint(sph[k].z), __float_as_uint(sph[k].r));
+                        e[1] = make_uint4(__float_as_uint(ps[k].w), (localBase + uint32_t(k) * 32u) | (((vpMask >> k) & 1u) << 16), sid[k], 0u);   // last iteration's descriptors are staged: D is free
                     }
                     qn += uint32_t(__popc(ball));
                 }
@@ -317,31 +314,41 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
         if (valid) {
             __syncwarp();
             // ---- S3: the warp evaluates its own survivors, 32 at a time: Hi-Z + LOD; emitters are compacted in place -----------------
+            uint32_t bitsK = 0u;                                   // lane k < ITEMS: new visibility mask of the span's k-th 32 objects
             for (uint32_t e0 = 0u; e0 < qn; e0 += 32u) {
                 const uint32_t e = e0 + lane;
                 uint32_t res = 0u, local = 0u;
                 if (e < qn) {
-                    const uint2 m = qMeta[e];
-                    local = m.y & 0xFFFFu;
-                    res = eval_entry<PASS, HIZ>(qSphere[e], m, qSurf[e], surfT, lodT, p);
-                    if (PASS == PASS_LATE) sVis[local - warp * uint32_t(WSPAN)] = res & 1u;
+                    const uint4 a = queue[2u * e], b = queue[2u * e + 1u];
+                    local = b.y & 0xFFFFu;
+                    res = eval_entry<PASS, HIZ>(make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w)),
+                                                make_uint2(b.x, b.y), b.z, surfT, lodT, p);
                 }
                 const uint32_t eb = __ballot_sync(0xFFFFFFFFu, (res & 2u) != 0u);
-                __syncwarp();                                      // every qSurf[e] of this round is read before wDesc (same words, lower or equal index) is written
-                if (res & 2u) wDesc[emitRun + uint32_t(__popc(eb & laneLt))] = local | ((res >> 2) << kSLocalBits);
+                if (res & 2u) reinterpret_cast<uint32_t*>(queue)[8u * (emitRun + uint32_t(__popc(eb & laneLt))) + 7u] = local | ((res >> 2) << kSLocalBits);
                 emitRun += uint32_t(__popc(eb));
+                if (PASS == PASS_LATE) {                           // the span's visibility as ITEMS mask words: OR of the visible entries' bits
+                    const uint32_t rel = local - warp * uint32_t(WSPAN);
+                    const uint32_t bit = (res & 1u) << (rel & 31u);
+#pragma unroll
+                    for (int k = 0; k < ITEMS; ++k) {
+                        const uint32_t w = __reduce_or_sync(0xFFFFFFFFu, (rel >> 5) == uint32_t(k) ? bit : 0u);
+                        if (lane == uint32_t(k)) bitsK |= w;
+                    }
+                }
             }
             if (lane == 0) s_warpCnt[ju & 1u][warp] = emitRun;
             if (PASS == PASS_LATE) {
-                __syncwarp();
+                // LateDrawCull.comp.glsl:70.  Visibility lives as a bit mask (one word per 32 consecutive objects): what the next early and
+                // late passes stream; the reference's u32-per-object form is written too when the caller asked for it (option vis_words)
+                const uint32_t firstObj = tileBase + warp * uint32_t(WSPAN);
+                if (lane < uint32_t(ITEMS) && firstObj + lane * 32u < p.n) p.visBits[(firstObj >> 5) + lane] = bitsK;
+                if (p.visibility != nullptr) {
 #pragma unroll
-                for (int k = 0; k < ITEMS; ++k) {                  // LateDrawCull.comp.glsl:70, coalesced
-                    const uint32_t v = ((survMask >> k) & 1u) ? sVis[lane + uint32_t(k) * 32u] : 0u;
-                    // visibility lives as a bit mask (one word per 32 consecutive objects): what the next early and late passes stream;
-                    // the reference's u32-per-object form is written too when the caller asked for it (option vis_words)
-                    if (p.visibility != nullptr && ((inMaskJ >> k) & 1u)) p.visibility[tileBase + localBase + uint32_t(k) * 32u] = v;
-                    const uint32_t vb = __ballot_sync(0xFFFFFFFFu, v != 0u);
-                    if (lane == 0 && ((inMaskJ >> k) & 1u)) p.visBits[(tileBase + localBase + uint32_t(k) * 32u) >> 5] = vb;
+                    for (int k = 0; k < ITEMS; ++k) {
+                        const uint32_t w = __shfl_sync(0xFFFFFFFFu, bitsK, k);
+                        if ((inMaskJ >> k) & 1u) p.visibility[tileBase + localBase + uint32_t(k) * 32u] = (w >> lane) & 1u;
+                    }
                 }
             }
         }
@@ -381,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
                 s_totals[ju & 3u] = total;
             }
             uint32_t* st = stageB + slot3 * TILE + warpOff;
-            for (uint32_t i = lane; i < emitRun; i += 32u) st[i] = wDesc[i];
+            for (uint32_t i = lane; i < emitRun; i += 32u) st[i] = reinterpret_cast<const uint32_t*>(queue)[8u * i + 7u];
         }
         if (prev2 != kNoTile) {
             const uint32_t total = s_totals[(ju - uint32_t(kLagS)) & 3u];
@@ -447,7 +454,7 @@ cudaError_t launch_cfg(const DrawCullParams& p, int numSMs, cudaStream_t stream)
     if (p.lodCount >= (1u << (30 - kSLocalBits))) return cudaErrorInvalidValue;     // descriptor packing (checked by the C-ABI layer too)
     const size_t tableBytes = (size_t(p.surfaceCount) + p.lodCount) * 32u;
     const bool smemTables = tableBytes <= 8192u;
-    const size_t smem = (smemTables ? tableBytes : 0u) + size_t(kStreamDepth) * VIS_STAGE_BYTES + size_t(TILE) * (size_t(kStreamDepth) * 8 + 16 + 8 + 4 + (PASS == PASS_LATE ? 4 : 0) + 4 * kStagesS);
+    const size_t smem = (smemTables ? tableBytes : 0u) + size_t(kStreamDepth) * VIS_STAGE_BYTES + size_t(TILE) * (size_t(kStreamDepth) * 8 + 32 + 4 * kStagesS);
     auto kernel = smemTables ? stream_cull_kernel<PASS, HIZ, THREADS, ITEMS, MINB, true> : stream_cull_kernel<PASS, HIZ, THREADS, ITEMS, MINB, false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
