@@ -350,6 +350,38 @@ def main():
         e2e = {"value": (n * world) / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
                "what": "blz_cull_upload_scene (pinned host arrays) + write_visibility + set_view + set_depth + early + read_draws + build_pyramid + late + read_draws, host wall clock"}
 
+    # ---- second end-to-end figure: the reference's OWN per-frame host traffic (UpdateBuffers, BlitzenVulkan/vulkanDraw.cpp:46-60: view
+    #      block + the dynamic transforms [0, 1000); the scene itself was uploaded once by SetupForRendering) + draw-list read-backs ------
+    e2e_frame = None
+    if not args.no_e2e:
+        ndyn = min(1000, len(xf_v))
+        ctx.write_visibility(h_vis.numpy().view(np.uint32))
+        times = []
+        for it in range(args.e2e_steps * 4 + 2):
+            barrier()
+            t0 = time.perf_counter()
+            ctx.update_transforms(0, xf_v[:ndyn])
+            ctx.set_view(w["view"])
+            ctx.early(capi.REC_VK24)
+            wv, tv = C.c_uint32(), C.c_uint32()
+            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, C.c_void_p(draws_v.ctypes.data), n, C.byref(wv), C.byref(tv)))
+            ctx.build_pyramid(variant)
+            ctx.late(capi.REC_VK24, variant)
+            wl, tl = C.c_uint32(), C.c_uint32()
+            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, C.c_void_p(draws_v.ctypes.data), n, C.byref(wl), C.byref(tl)))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it >= 2:
+                times.append(dt)
+        f_ms = 1e3 * float(np.mean(times))
+        if dist is not None:
+            tt = torch.tensor([f_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            f_ms = float(tt.item())
+        e2e_frame = {"value": (n * world) / (f_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(ndyn * 32 + 256), "d2h_bytes_per_step": int((wv.value + wl.value) * 24 + 16),
+                     "ms_per_step": f_ms, "what": "the reference's per-frame host traffic only (UpdateBuffers: view block + dynamic transforms [0,1000)), scene resident since "
+                     "blz_cull_upload_scene; early + read_draws + build_pyramid + late + read_draws, host wall clock. NOT the headline: `e2e` re-uploads the whole scene every step"}
+
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on the host cores -----------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -369,7 +401,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_frame": e2e_frame, "gpu_launches": int(launches),
                 "clocks": clocks,
                 "detail": {"visible_prev_frame": vis_prev, "early_draws": early_total, "late_draws": late_total,
                            "kernel_ms": {"early": t_early, "pyramid": t_pyr, "late": t_late}}}
