@@ -483,6 +483,9 @@ cudaError_t launch_pass(const DrawCullParams& p, int cfg, int numSMs, cudaStream
     case 6: return launch_cfg<PASS, HIZ, 256, 3, 4>(p, numSMs, stream);
     case 7: return launch_cfg<PASS, HIZ, 512, 3, 2>(p, numSMs, stream);
     case 8: return launch_cfg<PASS, HIZ, 128, 4, 7>(p, numSMs, stream);
+    case 9: return launch_cfg<PASS, HIZ, 256, 5, 2>(p, numSMs, stream);
+    case 10: return launch_cfg<PASS, HIZ, 256, 6, 2>(p, numSMs, stream);
+    case 11: return launch_cfg<PASS, HIZ, 384, 4, 2>(p, numSMs, stream);
     default: return launch_cfg<PASS, HIZ, 256, 2, 6>(p, numSMs, stream);
     }
 }
