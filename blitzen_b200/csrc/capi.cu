@@ -215,6 +215,32 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     return BLZ_OK;
 }
 
+// Step 1 of the survivor-list pipeline (cull_list.cu): the streaming frustum + LOD pass with 8-byte records {objectId, absolute LOD id};
+// the count stays on the device at counts[6].
+int run_survivor_list(blz_cull_ctx* c, int list)
+{
+    const uint32_t n = c->nObjs[list];
+    TRY_RC(grow(c, c->survList, c->capSurvList, size_t(n) * sizeof(uint2) + 16u));
+    DrawCullParams p{};
+    p.objs = c->objs[list]; p.n = n;
+    p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
+    p.visibility = nullptr; p.draws = reinterpret_cast<uint32_t*>(c->survList); p.counts = c->counts + 6; p.ctl = c->ctl;
+    p.numTiles = tiles_for(p.n);
+    TRY_RC(ensure_status(c, p.n / kCullMinTile + 2u));
+    p.status = c->status;
+    p.objectIdBase = list == BLZ_LIST_OPAQUE ? c->objectIdBase : 0u;
+    p.transformIdBase = c->transformIdBase;
+    p.surfaceCount = c->nSurf; p.lodCount = c->nLods;
+    p.recWords = 2u;
+    p.flags = c->optStreamDynamic ? kFlagDynamicTiles : 0u;
+    p.capacity = n;
+    p.view = make_view_consts(c->view);
+    p.pyr = c->pyr;
+    CU_TRY(launch_stream_cull(p, PASS_FRUSTUM, HIZ_VK, int(c->optStreamCfg), c->numSMs, c->stream));
+    c->launches++;
+    return BLZ_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -257,7 +283,7 @@ static void free_scene(blz_cull_ctx* c)
     for (int i = 0; i < 3; ++i) { dfree(c->objs[i]); c->nObjs[i] = 0; }
     dfree(c->xfPS); dfree(c->xfQ); dfree(c->xfStage); c->nXf = 0; c->xfStageCap = 0;
     dfree(c->surf); dfree(c->lods); dfree(c->clusters); dfree(c->lodInst); dfree(c->bucketCap);
-    dfree(c->vis); dfree(c->visList); dfree(c->visBits); dfree(c->draws); dfree(c->dispatch); dfree(c->instIdx);
+    dfree(c->vis); dfree(c->visList); dfree(c->visBits); dfree(c->draws); dfree(c->dispatch); dfree(c->instIdx); dfree(c->survList); dfree(c->listScratch); c->capSurvList = 0; c->capListScratch = 0;
     c->capVisList = 0; c->visListValid = false; c->capVisBits = 0; c->visBitsValid = false;
     c->nSurf = c->nLods = c->nClusters = c->nLodInst = 0; c->drawCap = c->dispatchCap = c->instCap = 0;
     c->capObjs[0] = c->capObjs[1] = c->capObjs[2] = 0;
@@ -524,6 +550,20 @@ int blz_cull_instanced(blz_cull_ctx* c, int list)
     if (!c->lodInst) return fail(BLZ_ERR_INVALID, "scene was uploaded without lod_instances");
     if (c->nLods > 256) return fail(BLZ_ERR_CAPACITY, "instancing supports at most 256 LODs (scene has %u)", c->nLods);
     CU_TRY(cudaSetDevice(c->device));
+    if (c->optListPipeline && c->nLods < (1u << 18)) {
+        TRY_RC(run_survivor_list(c, list));
+        TRY_RC(grow(c, c->listScratch, c->capListScratch, size_t(c->nLods) * kListMaxTiles * sizeof(uint32_t)));
+        ListInstanceParams q{};
+        q.list = c->survList; q.listCount = c->counts + 6; q.maxEntries = c->nObjs[list];
+        q.lodInstances = c->lodInst; q.bucketCapacity = c->bucketCap; q.instanceIndices = c->instIdx;
+        q.lods = c->lods; q.lodCount = c->nLods;
+        q.cmds = c->draws; q.counts = c->counts; q.cmdCapacity = c->drawCap;
+        q.hist = c->listScratch;
+        CU_TRY(launch_list_instancing(q, c->stream));
+        c->launches += 2;
+        c->lastRecWords = 8u;
+        return BLZ_OK;
+    }
     InstanceCullParams p{};
     p.objs = c->objs[list]; p.n = c->nObjs[list]; p.numTiles = tiles_for(p.n);
     p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
@@ -546,6 +586,18 @@ int blz_cull_cluster_expand(blz_cull_ctx* c, int list)
     int rc = check_list(c, list); if (rc) return rc;
     if (!c->dispatch) return fail(BLZ_ERR_INVALID, "scene was uploaded with cluster_dispatch_capacity = 0");
     CU_TRY(cudaSetDevice(c->device));
+    if (c->optListPipeline && c->nLods < (1u << 18)) {
+        TRY_RC(run_survivor_list(c, list));
+        TRY_RC(grow(c, c->listScratch, c->capListScratch, list_expand_scratch_words(c->nObjs[list], c->dispatchCap) * sizeof(uint32_t)));
+        ListExpandParams q{};
+        q.list = c->survList; q.listCount = c->counts + 6; q.maxEntries = c->nObjs[list];
+        q.lods = c->lods; q.lodCount = c->nLods;
+        q.dispatch = c->dispatch; q.counts = c->counts + 2; q.capacity = c->dispatchCap;
+        list_expand_carve(c->listScratch, c->nObjs[list], q); q.ctl = c->ctl;
+        CU_TRY(launch_list_expand(q, c->numSMs, c->stream));
+        c->launches += 2;
+        return BLZ_OK;
+    }
     ClusterExpandParams p{};
     p.objs = c->objs[list]; p.n = c->nObjs[list]; p.numTiles = tiles_for(p.n);
     p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
@@ -709,6 +761,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (strcmp(name, "early_bits") == 0) { c->optEarlyBits = value; return BLZ_OK; }
     if (strcmp(name, "vis_words") == 0) { c->optVisWords = value; return BLZ_OK; }
     if (strcmp(name, "draw_kernel") == 0) { c->optDrawKernel = value; return BLZ_OK; }
+    if (strcmp(name, "list_pipeline") == 0) { c->optListPipeline = value; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     if (strcmp(name, "stream_dynamic") == 0) { c->optStreamDynamic = value; return BLZ_OK; }
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);

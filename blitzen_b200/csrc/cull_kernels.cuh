@@ -82,6 +82,31 @@ struct ClusterCullParams {
     PyramidDesc pyr;
 };
 
+// survivor-list pipeline (cull_list.cu): step 1 = streaming frustum + LOD pass with recWords = 2 -> {objectId, absolute LOD id}
+constexpr uint32_t kListMaxTiles = 1024;   // tiles of the instancing step (bounds the per-tile histogram reduction)
+struct ListInstanceParams {
+    const uint2* list; const uint32_t* listCount;   // survivors, ascending objectId; count on the device
+    uint32_t maxEntries;                             // capacity of `list`
+    LodInstanceCounter* lodInstances; const uint32_t* bucketCapacity; uint32_t* instanceIndices;
+    const LodData* lods; uint32_t lodCount;
+    uint32_t* cmds; uint32_t* counts; uint64_t cmdCapacity;
+    uint32_t* hist;                                  // [lodCount][kListMaxTiles]
+};
+struct ListExpandParams {
+    const uint2* list; const uint32_t* listCount; uint32_t maxEntries;
+    const LodData* lods; uint32_t lodCount;
+    uint32_t* dispatch; uint32_t* counts; uint64_t capacity;
+    uint32_t* tileCount;                             // per tile of 2048 survivors: records
+    uint32_t* tilePrefix;                            // ... and their exclusive prefix
+    uint2* items;                                    // work items of the write step: {tile, slice of the tile's records}
+    uint32_t* numItems;
+    ScanCtl* ctl;
+};
+size_t list_expand_scratch_words(uint32_t maxEntries, uint64_t capacity);
+void list_expand_carve(uint32_t* scratch, uint32_t maxEntries, ListExpandParams& p);
+cudaError_t launch_list_instancing(const ListInstanceParams& p, cudaStream_t stream);
+cudaError_t launch_list_expand(const ListExpandParams& p, int numSMs, cudaStream_t stream);
+
 // launchers (return the cudaError_t of the launch)
 cudaError_t launch_draw_cull(const DrawCullParams& p, int pass, int hiz, int numSMs, cudaStream_t stream);
 cudaError_t launch_stream_cull(const DrawCullParams& p, int pass, int hiz, int cfg, int numSMs, cudaStream_t stream);   // cull_stream.cu

@@ -406,7 +406,10 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
                 uint2* dst = reinterpret_cast<uint2*>(p.draws + size_t(prefix) * p.recWords);
                 const uint32_t idBase = p.objectIdBase + prev2 * uint32_t(TILE);
                 // {objectId, indexCount} {instanceCount = 1, firstIndex} {vertexOffset = 0, firstInstance = 0} [{pad, pad}]
-                if (p.recWords == 6u) {
+                if (p.recWords == 2u) {
+                    // survivor-list form {objectId, absolute LOD id}: input of the instancing / cluster-expand kernels (cull_list.cu)
+                    for (uint32_t w = tid; w < nrec; w += THREADS) { const uint32_t d = st[w]; st_rec_u2(dst + w, make_uint2(idBase + (d & kSLocalMask), d >> kSLocalBits)); }
+                } else if (p.recWords == 6u) {
                     for (uint32_t w = tid; w < nrec * 3u; w += THREADS) {
                         const uint32_t r = w / 3u, f = w - r * 3u;
                         const uint32_t d = st[r];
