@@ -183,7 +183,7 @@ def workload_config(args, world):
     return {"workload": "configs[1]: stress-scene mesh mix replicated to 16777216 objects, two-phase frustum + Hi-Z (" + args.hiz.upper() +
                         " variant) + LOD cull, 1920x1080 synthetic depth, view " + VIEW_NAME,
             "objects_per_gpu": args.objects, "objects_total": args.objects * world, "depth": [DEPTH_W, DEPTH_H],
-            "step": "early pass + Hi-Z pyramid build + late pass" + (" + peer-memory draw-list gather (early and late lists)" if world > 1 else ""),
+            "step": "early pass + Hi-Z pyramid build + late pass" + (" + peer-memory draw-list gather (early and late lists, pushed on a side stream behind each pass)" if world > 1 else ""),
             "record_format": "VK24", "l2_policy": "inputs larger than L2 (object + transform streams = 40 B x 16.7 M = 671 MB >> 126 MB)",
             "parallelism": f"object-sharded x{world}"}
 
@@ -226,11 +226,11 @@ def main():
     def frame():
         ctx.early(capi.REC_VK24)
         if gather:
-            epoch[0] += 1; gather.push(epoch[0])
+            epoch[0] += 1; gather.push_async(epoch[0])
         ctx.build_pyramid(variant)
         ctx.late(capi.REC_VK24, variant)
         if gather:
-            epoch[0] += 1; gather.push(epoch[0])
+            epoch[0] += 1; gather.push_async(epoch[0])
 
     # frame 0 (cleared pyramid, visibility 0) then warm-up frames: establishes the steady-state visibility buffer
     ctx.clear_pyramid(variant, DEPTH_W, DEPTH_H)
@@ -259,14 +259,16 @@ def main():
             ev[k][0].record(stream)
             ctx.early(capi.REC_VK24)
             if gather:
-                epoch[0] += 1; gather.push(epoch[0])
+                epoch[0] += 1; gather.push_async(epoch[0])
             ev[k][1].record(stream)
             ctx.build_pyramid(variant)
             ev[k][2].record(stream)
             ctx.late(capi.REC_VK24, variant)
             ev[k][3].record(stream)
             if gather:
-                epoch[0] += 1; gather.push(epoch[0])
+                epoch[0] += 1; gather.push_async(epoch[0])
+        if gather:
+            ctx.gather_join()            # the timed region ends when the last side-stream push has landed on the presenter
         t_end.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -360,7 +362,7 @@ def main():
         for it in range(args.e2e_steps * 4 + 2):
             barrier()
             t0 = time.perf_counter()
-            ctx.update_transforms(0, xf_v[:ndyn])
+            ctx.update_transforms(w["transform_id_base"], xf_v[:ndyn])       # the first 1000 transforms this rank owns (global ids)
             ctx.set_view(w["view"])
             ctx.early(capi.REC_VK24)
             wv, tv = C.c_uint32(), C.c_uint32()

@@ -64,7 +64,7 @@ ABI_SYMBOLS = [
     "blz_cull_temporal", "blz_cull_instanced", "blz_cull_cluster_expand", "blz_cull_cluster_cull",
     "blz_cull_set_cluster_dispatch", "blz_cull_get_outputs", "blz_cull_read_draws", "blz_cull_read_count",
     "blz_cull_read_visibility", "blz_cull_read_cluster_dispatch", "blz_cull_read_instances", "blz_cull_read_pyramid",
-    "blz_cull_gather_export", "blz_cull_gather_import", "blz_cull_gather_configure", "blz_cull_gather_push",
+    "blz_cull_gather_export", "blz_cull_gather_import", "blz_cull_gather_configure", "blz_cull_gather_push", "blz_cull_gather_push_async", "blz_cull_gather_join",
     "blz_cull_gather_read", "blz_cull_gather_outputs", "blz_cull_launch_count", "blz_cull_set_option",
 ]
 
@@ -97,7 +97,7 @@ def load_library():
         "blz_cull_read_cluster_dispatch": [vp, vp, u64, C.POINTER(u32), C.POINTER(u32)],
         "blz_cull_read_instances": [vp, vp, u64, vp], "blz_cull_read_pyramid": [vp, vp, u64, vp, vp],
         "blz_cull_gather_export": [vp, u64, i, vp], "blz_cull_gather_import": [vp, vp, i, i],
-        "blz_cull_gather_configure": [vp, u64, i], "blz_cull_gather_push": [vp, u32],
+        "blz_cull_gather_configure": [vp, u64, i], "blz_cull_gather_push": [vp, u32], "blz_cull_gather_push_async": [vp, u32], "blz_cull_gather_join": [vp],
         "blz_cull_gather_read": [vp, u32, vp, u64, vp], "blz_cull_gather_outputs": [vp, C.POINTER(vp), C.POINTER(vp)],
         "blz_cull_launch_count": [vp, C.POINTER(u64)], "blz_cull_set_option": [vp, C.c_char_p, C.c_int64],
     }
@@ -322,6 +322,12 @@ class CullContext:
 
     def gather_push(self, epoch):
         self._check(self._lib.blz_cull_gather_push(self._h, int(epoch)))
+
+    def gather_push_async(self, epoch):
+        self._check(self._lib.blz_cull_gather_push_async(self._h, int(epoch)))
+
+    def gather_join(self):
+        self._check(self._lib.blz_cull_gather_join(self._h))
 
     def gather_read(self, epoch, world, fmt=REC_VK24, capacity=None):
         counts = np.zeros(world, dtype=np.uint32)

@@ -177,7 +177,7 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     DrawCullParams p{};
     p.objs = c->objs[list]; p.n = c->nObjs[list];
     p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
-    p.visibility = c->vis; p.draws = c->draws; p.counts = c->counts; p.ctl = c->ctl;
+    p.visibility = c->vis; p.draws = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
     p.numTiles = tiles_for(p.n);                      // re-derived from `items` by the launcher
     rc = ensure_status(c, p.n / kCullMinTile + 2u); if (rc) return rc;
     p.status = c->status;
@@ -269,8 +269,9 @@ int blz_cull_create(int device, blz_cull_ctx** out)
     CU_TRY(cudaMalloc(&c->ctl, sizeof(ScanCtl)));
     ScanCtl init{ 0u, 0u, 1u, 0u };
     CU_TRY(cudaMemcpyAsync(c->ctl, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(cudaMalloc(&c->counts, 8 * sizeof(uint32_t)));
-    CU_TRY(cudaMemsetAsync(c->counts, 0, 8 * sizeof(uint32_t), c->stream));
+    CU_TRY(cudaMalloc(&c->counts, 16 * sizeof(uint32_t)));
+    CU_TRY(cudaMemsetAsync(c->counts, 0, 16 * sizeof(uint32_t), c->stream));
+    c->drawCounts = c->counts;
     CU_TRY(cudaMalloc(&c->pyrTicket, sizeof(uint32_t)));
     CU_TRY(cudaMemsetAsync(c->pyrTicket, 0, sizeof(uint32_t), c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -283,7 +284,7 @@ static void free_scene(blz_cull_ctx* c)
     for (int i = 0; i < 3; ++i) { dfree(c->objs[i]); c->nObjs[i] = 0; }
     dfree(c->xfPS); dfree(c->xfQ); dfree(c->xfStage); c->nXf = 0; c->xfStageCap = 0;
     dfree(c->surf); dfree(c->lods); dfree(c->clusters); dfree(c->lodInst); dfree(c->bucketCap);
-    dfree(c->vis); dfree(c->visList); dfree(c->visBits); dfree(c->draws); dfree(c->dispatch); dfree(c->instIdx); dfree(c->survList); dfree(c->listScratch); c->capSurvList = 0; c->capListScratch = 0;
+    dfree(c->vis); dfree(c->visList); dfree(c->visBits); dfree(c->draws); dfree(c->drawsAlt); dfree(c->dispatch); dfree(c->instIdx); dfree(c->survList); dfree(c->listScratch); c->capSurvList = 0; c->capListScratch = 0;
     c->capVisList = 0; c->visListValid = false; c->capVisBits = 0; c->visBitsValid = false;
     c->nSurf = c->nLods = c->nClusters = c->nLodInst = 0; c->drawCap = c->dispatchCap = c->instCap = 0;
     c->capObjs[0] = c->capObjs[1] = c->capObjs[2] = 0;
@@ -296,6 +297,7 @@ int blz_cull_destroy(blz_cull_ctx* c)
     if (!c) return BLZ_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->gatherStream) cudaStreamSynchronize(c->gatherStream);
     free_scene(c);
     dfree(c->ctl); dfree(c->status); dfree(c->counts); dfree(c->depthOwned); dfree(c->pyrData); dfree(c->pyrTicket);
     blz::gather_release(c);
@@ -320,6 +322,7 @@ int blz_cull_synchronize(blz_cull_ctx* c)
     if (!c) return fail(BLZ_ERR_INVALID, "null context");
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    if (c->gatherStream) CU_TRY(cudaStreamSynchronize(c->gatherStream));
     return BLZ_OK;
 }
 
@@ -387,7 +390,12 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     c->visBitsValid = true; c->visWordsValid = true;
     // draw buffer (sized for the wider DX32 record), cluster dispatch buffer
     c->drawCap = d->draw_capacity ? d->draw_capacity : (maxList ? maxList : 1);
-    TRY_RC(grow(c, c->draws, c->capDraws, size_t(c->drawCap) * 8u * sizeof(uint32_t)));
+    {
+        if (c->gatherStream) CU_TRY(cudaStreamSynchronize(c->gatherStream));
+        const size_t before = c->capDraws;
+        TRY_RC(grow(c, c->draws, c->capDraws, size_t(c->drawCap) * 8u * sizeof(uint32_t)));
+        if (c->capDraws != before && c->drawsAlt) { cudaFree(c->drawsAlt); c->drawsAlt = nullptr; }   // re-created by the next asynchronous push
+    }
     c->dispatchCap = d->cluster_dispatch_capacity;
     if (c->dispatchCap) TRY_RC(grow(c, c->dispatch, c->capDispatch, size_t(c->dispatchCap) * 3u * sizeof(uint32_t)));
     // instancing
@@ -557,7 +565,7 @@ int blz_cull_instanced(blz_cull_ctx* c, int list)
         q.list = c->survList; q.listCount = c->counts + 6; q.maxEntries = c->nObjs[list];
         q.lodInstances = c->lodInst; q.bucketCapacity = c->bucketCap; q.instanceIndices = c->instIdx;
         q.lods = c->lods; q.lodCount = c->nLods;
-        q.cmds = c->draws; q.counts = c->counts; q.cmdCapacity = c->drawCap;
+        q.cmds = c->draws; q.counts = c->drawCounts; q.cmdCapacity = c->drawCap;
         q.hist = c->listScratch;
         CU_TRY(launch_list_instancing(q, c->stream));
         c->launches += 2;
@@ -568,7 +576,7 @@ int blz_cull_instanced(blz_cull_ctx* c, int list)
     p.objs = c->objs[list]; p.n = c->nObjs[list]; p.numTiles = tiles_for(p.n);
     p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
     p.lodInstances = c->lodInst; p.bucketCapacity = c->bucketCap; p.instanceIndices = c->instIdx;
-    p.cmds = c->draws; p.counts = c->counts; p.ctl = c->ctl;
+    p.cmds = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
     rc = ensure_status(c, size_t(p.numTiles) * c->nLods); if (rc) return rc;
     p.status = c->status;
     p.objectIdBase = list == BLZ_LIST_OPAQUE ? c->objectIdBase : 0u; p.transformIdBase = c->transformIdBase;
@@ -625,7 +633,7 @@ int blz_cull_cluster_cull(blz_cull_ctx* c, int mode, int fmt, int hiz)
     ClusterCullParams p{};
     p.dispatch = c->dispatch; p.dispatchCount = c->counts + 2;
     p.objs = c->objs[BLZ_LIST_OPAQUE]; p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.clusters = c->clusters;
-    p.draws = c->draws; p.counts = c->counts; p.ctl = c->ctl;
+    p.draws = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
     p.maxRecords = uint32_t(c->dispatchCap > 0xFFFFFFFFull ? 0xFFFFFFFFull : c->dispatchCap);
     int rc = ensure_status(c, tiles_for(p.maxRecords)); if (rc) return rc;
     p.status = c->status;
@@ -655,7 +663,7 @@ int blz_cull_get_outputs(blz_cull_ctx* c, blz_outputs* o)
     if (!c || !o) return fail(BLZ_ERR_INVALID, "null argument");
     memset(o, 0, sizeof(*o));
     if (c->vis && c->nObjs[0]) TRY_RC(ensure_vis_words(c));                  // the u32 view is materialised on demand (stream-ordered)
-    o->draws = c->draws; o->draw_count = c->counts; o->visibility = c->vis;
+    o->draws = c->draws; o->draw_count = c->drawCounts; o->visibility = c->vis;
     o->cluster_dispatch = c->dispatch; o->cluster_count = c->counts ? c->counts + 2 : nullptr;
     o->instance_indices = c->instIdx; o->instance_counts = reinterpret_cast<uint32_t*>(c->lodInst);
     o->pyramid = c->pyrData; o->pyramid_width = c->pyr.width; o->pyramid_height = c->pyr.height; o->pyramid_mips = c->pyr.mips;
@@ -669,7 +677,7 @@ int blz_cull_read_count(blz_cull_ctx* c, uint32_t* written, uint32_t* total)
     if (!c) return fail(BLZ_ERR_INVALID, "null context");
     CU_TRY(cudaSetDevice(c->device));
     uint32_t h[2];
-    CU_TRY(cudaMemcpyAsync(h, c->counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(h, c->drawCounts, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (written) *written = h[0];
     if (total) *total = h[1];
@@ -698,7 +706,7 @@ static int read_records(blz_cull_ctx* c, const uint32_t* dev, const uint32_t* de
 int blz_cull_read_draws(blz_cull_ctx* c, void* host, uint64_t cap, uint32_t* written, uint32_t* total)
 {
     if (!c || !c->draws) return fail(BLZ_ERR_INVALID, "no scene uploaded");
-    return read_records(c, c->draws, c->counts, c->lastRecWords, host, cap, written, total);
+    return read_records(c, c->draws, c->drawCounts, c->lastRecWords, host, cap, written, total);
 }
 
 int blz_cull_read_visibility(blz_cull_ctx* c, uint32_t* host)

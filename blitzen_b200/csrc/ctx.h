@@ -24,7 +24,8 @@ struct blz_cull_ctx {
     // per-object state + outputs
     uint32_t* vis = nullptr;
     uint32_t* draws = nullptr; uint64_t drawCap = 0;
-    uint32_t* counts = nullptr;               // [0..1] draws, [2..3] cluster dispatch, [4] length of visList
+    uint32_t* counts = nullptr;               // [0..1] draws (slot 0), [2..3] cluster dispatch, [4] length of visList, [6..7] survivor list, [8..9] draws (slot 1)
+    uint32_t* drawCounts = nullptr;           // counts + 0 or counts + 8: {written, total} of the current draw buffer
     uint32_t* visList = nullptr; size_t capVisList = 0;   // ascending ids the last late pass found visible
     uint32_t* visBits = nullptr; size_t capVisBits = 0;   // 1 bit per object, padded to whole early-pass tiles
     bool visBitsValid = false;                // visBits is current
@@ -59,6 +60,9 @@ struct blz_cull_ctx {
     uint32_t* gatherBuf = nullptr; uint64_t gatherCap = 0; uint32_t gatherRecWords = 6; uint64_t* gatherFlags = nullptr; bool gatherOwner = false;
     uint32_t* gatherDst = nullptr; uint64_t* gatherDstFlags = nullptr; int rank = 0, world = 1; bool gatherImported = false, gatherPeerMapped = false;
     uint32_t* gatherDone = nullptr;
+    // asynchronous push: the list just pushed stays readable in `drawsAlt` while the next pass writes `draws` (blz_cull_gather_push_async)
+    uint32_t* drawsAlt = nullptr; uint32_t lastRecWordsAlt = 6; int drawSlot = 0;
+    cudaStream_t gatherStream = nullptr; cudaEvent_t evCull = nullptr, evPush[2] = { nullptr, nullptr }; bool evPushValid[2] = { false, false };
 };
 
 namespace blz {

@@ -21,7 +21,9 @@ constexpr int kDoneRow = kEpochSlots;
 constexpr int kFlagWords = (kEpochSlots + 1) * kFlagStride;
 // Epochs are consecutive integers starting at 1.  A rank may run ahead of a slower one (nothing on the host orders the
 // pushes of different ranks), so the count words are kept per epoch in a ring of 4 rows and a rank does not publish epoch e
-// before every rank has finished epoch e - 3: a word is never overwritten while somebody still waits for it.
+// before every rank has finished epoch e - 2: a word is never overwritten while somebody still waits for it.  The gather buffer has
+// two halves, epoch e goes to half e & 1: the list of epoch e stays intact while epoch e + 1 is being gathered (the early list is
+// still being drawn while the late list arrives); the consumer must be through with it before the ranks push epoch e + 2.
 
 __device__ __forceinline__ void st_release_sys_u64(uint64_t* p, uint64_t v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p)
@@ -48,9 +50,9 @@ __global__ void __launch_bounds__(kGatherThreads) gather_push_kernel(const Gathe
     if (tid == 0) {
         uint64_t* row = p.flags + (p.epoch % uint32_t(kEpochSlots)) * kFlagStride;
         if (blockIdx.x == 0) {
-            if (p.epoch > uint32_t(kEpochSlots - 1))                       // back-pressure: everybody is done with epoch e - 3
+            if (p.epoch > 2u)                                              // back-pressure: everybody is done with epoch e - 2 (same half of the gather buffer)
                 for (uint32_t r = 0; r < p.world; ++r)
-                    while (int32_t(uint32_t(ld_acquire_sys_u64(p.flags + kDoneRow * kFlagStride + r)) - (p.epoch - uint32_t(kEpochSlots - 1))) < 0) { }
+                    while (int32_t(uint32_t(ld_acquire_sys_u64(p.flags + kDoneRow * kFlagStride + r)) - (p.epoch - 2u)) < 0) { }
             st_release_sys_u64(row + p.rank, (uint64_t(p.epoch) << 32) | count);
         }
         uint64_t off = 0;
@@ -96,6 +98,7 @@ void gather_release(blz_cull_ctx* c)
     }
     if (c->gatherOwner) { if (c->gatherBuf) cudaFree(c->gatherBuf); if (c->gatherFlags) cudaFree(c->gatherFlags); }
     if (c->gatherDone) cudaFree(c->gatherDone);
+    if (c->gatherStream) { cudaStreamSynchronize(c->gatherStream); cudaStreamDestroy(c->gatherStream); cudaEventDestroy(c->evCull); cudaEventDestroy(c->evPush[0]); cudaEventDestroy(c->evPush[1]); c->gatherStream = nullptr; c->evPushValid[0] = c->evPushValid[1] = false; }
     c->gatherBuf = nullptr; c->gatherFlags = nullptr; c->gatherDst = nullptr; c->gatherDstFlags = nullptr; c->gatherDone = nullptr;
     c->gatherOwner = c->gatherImported = c->gatherPeerMapped = false;
 }
@@ -114,7 +117,7 @@ int blz_cull_gather_export(blz_cull_ctx* c, uint64_t capacityRecords, int fmt, v
     gather_release(c);
     c->gatherRecWords = fmt == BLZ_REC_VK24 ? 6u : 8u;
     c->gatherCap = capacityRecords;
-    CU_TRY(cudaMalloc(&c->gatherBuf, size_t(capacityRecords) * c->gatherRecWords * 4u));
+    CU_TRY(cudaMalloc(&c->gatherBuf, 2u * size_t(capacityRecords) * c->gatherRecWords * 4u));   // two halves: epoch parity
     CU_TRY(cudaMalloc(&c->gatherFlags, kFlagWords * sizeof(uint64_t)));
     CU_TRY(cudaMemset(c->gatherFlags, 0, kFlagWords * sizeof(uint64_t)));
     c->gatherOwner = true;
@@ -160,18 +163,67 @@ int blz_cull_gather_configure(blz_cull_ctx* c, uint64_t capacityRecords, int fmt
     return BLZ_OK;
 }
 
-int blz_cull_gather_push(blz_cull_ctx* c, uint32_t epoch)
+static int gather_launch(blz_cull_ctx* c, uint32_t epoch, cudaStream_t stream, int grid)
+{
+    GatherParams p{};
+    p.src = c->draws; p.srcCount = c->drawCounts; p.flags = c->gatherDstFlags; p.done = c->gatherDone;
+    p.dst = c->gatherDst + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords;
+    p.capacity = c->gatherCap; p.recWords = c->gatherRecWords; p.rank = uint32_t(c->rank); p.world = uint32_t(c->world); p.epoch = epoch;
+    gather_push_kernel<<<grid, kGatherThreads, 0, stream>>>(p);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return BLZ_OK;
+}
+
+static int gather_check(blz_cull_ctx* c, uint32_t epoch)
 {
     if (!c || !c->gatherImported) return fail(BLZ_ERR_INVALID, "gather not set up (export/import first)");
     if (epoch == 0) return fail(BLZ_ERR_INVALID, "epoch must be non-zero and change every push");
     if (c->lastRecWords != c->gatherRecWords) return fail(BLZ_ERR_INVALID, "last pass wrote %u-word records, gather buffer holds %u-word records", c->lastRecWords, c->gatherRecWords);
+    return BLZ_OK;
+}
+
+int blz_cull_gather_push(blz_cull_ctx* c, uint32_t epoch)
+{
+    int rc = gather_check(c, epoch); if (rc) return rc;
     CU_TRY(cudaSetDevice(c->device));
-    GatherParams p{};
-    p.src = c->draws; p.srcCount = c->counts; p.dst = c->gatherDst; p.flags = c->gatherDstFlags; p.done = c->gatherDone;
-    p.capacity = c->gatherCap; p.recWords = c->gatherRecWords; p.rank = uint32_t(c->rank); p.world = uint32_t(c->world); p.epoch = epoch;
-    gather_push_kernel<<<c->numSMs * 2, kGatherThreads, 0, c->stream>>>(p);
-    CU_TRY(cudaGetLastError());
-    c->launches++;
+    return gather_launch(c, epoch, c->stream, c->numSMs * 2);
+}
+
+// Same push, off the critical path: it runs on a side stream behind the pass that produced the list, and the context flips to its
+// second draw buffer (+ count words), so the NEXT pass on the main stream overlaps the NVLink transfer instead of waiting for it.
+// After the call `draws` / `draw_count` (blz_cull_get_outputs, blz_cull_read_draws) refer to the buffer the next pass will write;
+// the pushed list is on the presenter (blz_cull_gather_read).  A pass that would overwrite a buffer still being pushed waits for it.
+int blz_cull_gather_push_async(blz_cull_ctx* c, uint32_t epoch)
+{
+    int rc = gather_check(c, epoch); if (rc) return rc;
+    CU_TRY(cudaSetDevice(c->device));
+    if (!c->gatherStream) {
+        CU_TRY(cudaStreamCreateWithFlags(&c->gatherStream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&c->evCull, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->evPush[0], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->evPush[1], cudaEventDisableTiming));
+    }
+    if (!c->drawsAlt) CU_TRY(cudaMalloc(&c->drawsAlt, c->capDraws));
+    CU_TRY(cudaEventRecord(c->evCull, c->stream));
+    CU_TRY(cudaStreamWaitEvent(c->gatherStream, c->evCull, 0));
+    rc = gather_launch(c, epoch, c->gatherStream, 64); if (rc) return rc;      // 64 CTAs saturate an NVLink port and leave the SMs to the next pass
+    CU_TRY(cudaEventRecord(c->evPush[c->drawSlot], c->gatherStream));
+    c->evPushValid[c->drawSlot] = true;
+    uint32_t* t = c->draws; c->draws = c->drawsAlt; c->drawsAlt = t;
+    const uint32_t w = c->lastRecWords; c->lastRecWords = c->lastRecWordsAlt; c->lastRecWordsAlt = w;
+    c->drawSlot ^= 1;
+    c->drawCounts = c->counts + (c->drawSlot ? 8 : 0);
+    if (c->evPushValid[c->drawSlot]) CU_TRY(cudaStreamWaitEvent(c->stream, c->evPush[c->drawSlot], 0));   // that buffer's previous push
+    return BLZ_OK;
+}
+
+// makes the context's main stream wait for every asynchronous push issued so far (stream-ordered, no host synchronisation)
+int blz_cull_gather_join(blz_cull_ctx* c)
+{
+    if (!c) return fail(BLZ_ERR_INVALID, "null context");
+    CU_TRY(cudaSetDevice(c->device));
+    for (int k = 0; k < 2; ++k) if (c->evPushValid[k]) CU_TRY(cudaStreamWaitEvent(c->stream, c->evPush[k], 0));
     return BLZ_OK;
 }
 
@@ -191,7 +243,7 @@ int blz_cull_gather_read(blz_cull_ctx* c, uint32_t epoch, void* recordsHost, uin
     if (recordsHost) {
         uint64_t n = total < capacityRecords ? total : capacityRecords;
         if (n) {
-            CU_TRY(cudaMemcpyAsync(recordsHost, c->gatherBuf, size_t(n) * c->gatherRecWords * 4u, cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(cudaMemcpyAsync(recordsHost, c->gatherBuf + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords, size_t(n) * c->gatherRecWords * 4u, cudaMemcpyDeviceToHost, c->stream));
             CU_TRY(cudaStreamSynchronize(c->stream));
         }
     }

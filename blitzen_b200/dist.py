@@ -48,6 +48,10 @@ class DrawListGather:
     def push(self, epoch):
         self.ctx.gather_push(epoch)
 
+    def push_async(self, epoch):
+        """Push on a side stream; the context flips to its second draw buffer so the next pass overlaps the transfer."""
+        self.ctx.gather_push_async(epoch)
+
     def read(self, epoch):
         if self.rank != self.presenter:
             raise RuntimeError("only the presenting rank reads the gathered list")

@@ -194,6 +194,11 @@ int blz_cull_gather_import(blz_cull_ctx* ctx, const void* presenter_blob128, int
 /* ranks that did not export learn the presenter buffer's capacity / record format from the host layer */
 int blz_cull_gather_configure(blz_cull_ctx* ctx, uint64_t capacity_records, int record_format);
 int blz_cull_gather_push(blz_cull_ctx* ctx, uint32_t epoch);
+/* same push on a side stream: the context flips to its second draw buffer so the next pass overlaps the NVLink transfer; afterwards
+ * `draws` / `draw_count` refer to the buffer the next pass will write.  The presenter's gather buffer has two halves (epoch parity):
+ * the list of epoch e stays intact while epoch e + 1 arrives. */
+int blz_cull_gather_push_async(blz_cull_ctx* ctx, uint32_t epoch);
+int blz_cull_gather_join(blz_cull_ctx* ctx);   /* main stream waits for the asynchronous pushes issued so far (stream-ordered) */
 int blz_cull_gather_read(blz_cull_ctx* ctx, uint32_t epoch, void* records_host, uint64_t capacity_records, uint32_t* out_counts /* world entries */);
 int blz_cull_gather_outputs(blz_cull_ctx* ctx, void** out_records_device, uint32_t** out_flags_device);
 

@@ -54,6 +54,15 @@ def main():
     if rank == 0:
         results["late1"] = gather.read(epoch)
     dist.barrier()
+    # the same frame again with ASYNCHRONOUS pushes (side stream, double-buffered draw lists): early list of epoch e must still be
+    # intact on the presenter after the late list of epoch e + 1 has arrived (two halves of the gather buffer)
+    ctx.early(); epoch += 1; e_early = epoch; gather.push_async(epoch)
+    ctx.build_pyramid(capi.HIZ_VK); ctx.late(); epoch += 1; e_late = epoch; gather.push_async(epoch)
+    ctx.synchronize(); dist.barrier()
+    if rank == 0:
+        results["early2_async"] = gather.read(e_early)
+        results["late2_async"] = gather.read(e_late)
+    dist.barrier()
     ok = True
     if rank == 0:
         import oracle_lib as O
@@ -67,7 +76,9 @@ def main():
         exp["late0"], _, vis = O.cull(*S, O.PASS_LATE, pyramid=O.cleared_pyramid(1280, 720, O.HIZ_VK), vis=vis, **kw)
         exp["early1"], _, _ = O.cull(*S, O.PASS_EARLY, vis=vis, **kw)
         exp["late1"], _, vis = O.cull(*S, O.PASS_LATE, pyramid=O.build_pyramid(depth, O.HIZ_VK), vis=vis, **kw)
-        for k in ("frustum", "late0", "early1", "late1"):
+        exp["early2_async"], _, _ = O.cull(*S, O.PASS_EARLY, vis=vis, **kw)
+        exp["late2_async"], _, vis = O.cull(*S, O.PASS_LATE, pyramid=O.build_pyramid(depth, O.HIZ_VK), vis=vis, **kw)
+        for k in ("frustum", "late0", "early1", "late1", "early2_async", "late2_async"):
             recs, counts = results[k]
             got = recs.view(np.uint32).reshape(-1, 6)
             same = got.shape == exp[k].shape and np.array_equal(got, exp[k])
