@@ -635,7 +635,7 @@ int blz_cull_cluster_cull(blz_cull_ctx* c, int mode, int fmt, int hiz)
     p.objs = c->objs[BLZ_LIST_OPAQUE]; p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.clusters = c->clusters;
     p.draws = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
     p.maxRecords = uint32_t(c->dispatchCap > 0xFFFFFFFFull ? 0xFFFFFFFFull : c->dispatchCap);
-    int rc = ensure_status(c, tiles_for(p.maxRecords)); if (rc) return rc;
+    int rc = ensure_status(c, size_t(p.maxRecords) / kCullMinTile + 2u); if (rc) return rc;   // the kernel's tile is 512..1024 records (launch_cluster_cull)
     p.status = c->status;
     p.objectIdBase = c->objectIdBase; p.transformIdBase = c->transformIdBase; p.clusterCount = c->nClusters;
     p.recWords = fmt == BLZ_REC_VK24 ? 6u : 8u; p.mode = uint32_t(mode); p.capacity = c->drawCap;

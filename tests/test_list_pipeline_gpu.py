@@ -131,3 +131,26 @@ def test_cluster_expand_medium_then_cull(capi, medium_scene):
         ctx.cluster_cull(capi.CLUSTER_SPHERE, capi.REC_VK24)
         draws, dtot = ctx.read_draws(capi.REC_VK24)
         assert dtot == tot and np.array_equal(recs_u32(draws), exp)
+
+
+def test_cluster_cull_tight_capacity_all_modes(capi, small_scene):
+    """Dispatch buffer exactly as long as the record list (regression: the per-tile status array was sized for 1024-record tiles while
+    the Hi-Z variant of the cluster cull uses 768-record tiles -> out-of-bounds once the list filled more than 3/4 of the capacity)."""
+    sc = small_scene
+    view = view_at(**VIEWS["outside_all"])
+    d_all, d_tot = O.cluster_expand(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, 10_000_000)
+    assert d_tot == len(d_all) > 300_000
+    from blitzen_b200 import scene
+    depth = scene.synthetic_depth(640, 360, n_rects=40, z_min=20.0, z_max=300.0, seed=5)
+    pyr = O.build_pyramid(depth, 0)
+    with make_ctx(capi, sc, cluster_dispatch_capacity=d_tot, draw_capacity=d_tot) as ctx:
+        ctx.set_view(view); ctx.set_depth(depth); ctx.build_pyramid(0)
+        ctx.cluster_expand()
+        got, gtot = ctx.read_cluster_dispatch()
+        assert gtot == d_tot and np.array_equal(got.view(np.uint32).reshape(-1, 3), d_all)
+        for mode, kw in ((capi.CLUSTER_SPHERE_HIZ, dict(hiz=0, pyramid=pyr)), (capi.CLUSTER_SPHERE, {}), (capi.CLUSTER_PASSTHROUGH, {})):
+            exp, tot = O.cluster_cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], sc["clusters"], view, d_all,
+                                      0 if mode == capi.CLUSTER_PASSTHROUGH else 1, **kw)
+            ctx.cluster_cull(mode, capi.REC_VK24, 0)
+            draws, dtot = ctx.read_draws(capi.REC_VK24)
+            assert dtot == tot and np.array_equal(recs_u32(draws), exp), mode
