@@ -8,6 +8,7 @@
 // No NCCL call and no host round trip on the data path; NCCL (torch.distributed) only carries the 128-byte IPC handle
 // blob at set-up time (blitzen_b200/dist.py).
 #include "ctx.h"
+#include <cstdlib>
 #include <cstring>
 
 namespace blz {
@@ -70,7 +71,18 @@ __global__ void __launch_bounds__(kGatherThreads) gather_push_kernel(const Gathe
     const uint64_t n64 = nrec * (p.recWords >> 1);
     const uint2* src = reinterpret_cast<const uint2*>(p.src);
     uint2* dst = reinterpret_cast<uint2*>(p.dst + off * p.recWords);
-    for (uint64_t j = uint64_t(blockIdx.x) * kGatherThreads + tid; j < n64; j += uint64_t(gridDim.x) * kGatherThreads) dst[j] = src[j];
+    // eight independent loads in flight per thread: with one, a CTA moves 256 x 8 B per local-memory round trip (measured 3.7 GB/s per
+    // CTA -- the push was load-latency-bound, not NVLink-bound)
+    const uint64_t stride = uint64_t(gridDim.x) * kGatherThreads;
+    uint64_t j = uint64_t(blockIdx.x) * kGatherThreads + tid;
+    for (; j + 7ull * stride < n64; j += 8ull * stride) {
+        uint2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = src[j + uint64_t(u) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dst[j + uint64_t(u) * stride] = v[u];
+    }
+    for (; j < n64; j += stride) dst[j] = src[j];
     __threadfence_system();
     __syncthreads();
     if (tid == 0) {
@@ -207,7 +219,12 @@ int blz_cull_gather_push_async(blz_cull_ctx* c, uint32_t epoch)
     if (!c->drawsAlt) CU_TRY(cudaMalloc(&c->drawsAlt, c->capDraws));
     CU_TRY(cudaEventRecord(c->evCull, c->stream));
     CU_TRY(cudaStreamWaitEvent(c->gatherStream, c->evCull, 0));
-    rc = gather_launch(c, epoch, c->gatherStream, 64); if (rc) return rc;      // 64 CTAs saturate an NVLink port and leave the SMs to the next pass
+    // few CTAs: the presenter's NVLink ingest (900 GB/s) is shared by world - 1 pushers, and every resident push CTA takes a slot away
+    // from the pass running next to it on the main stream
+    static const int envCtas = [] { const char* e = getenv("BLZ_GATHER_CTAS"); return e ? atoi(e) : 0; }();
+    int ctas = envCtas > 0 ? envCtas : 56 / (c->world > 1 ? c->world - 1 : 1);        // measured at 8 GPUs: 8 CTAs 0.317 ms/frame, 16: 0.329, 32: 0.346
+    ctas = ctas < 4 ? 4 : (ctas > 32 ? 32 : ctas);
+    rc = gather_launch(c, epoch, c->gatherStream, ctas); if (rc) return rc;
     CU_TRY(cudaEventRecord(c->evPush[c->drawSlot], c->gatherStream));
     c->evPushValid[c->drawSlot] = true;
     uint32_t* t = c->draws; c->draws = c->drawsAlt; c->drawsAlt = t;
