@@ -329,7 +329,7 @@ def main():
             barrier()
             t0 = time.perf_counter()
             ctx.upload_scene(objs_v, xf_v, w["surfaces"], w["lods"], object_id_base=w["object_id_base"], transform_id_base=w["transform_id_base"])
-            ctx.write_visibility(h_vis.numpy().view(np.uint32))
+            ctx.write_visibility(h_vis.numpy().view(np.uint32))     # upload_scene resets the per-object state: last frame's visibility travels with the scene
             ctx.set_view(w["view"])
             ctx.set_depth(depth_v)
             ctx.early(capi.REC_VK24)
