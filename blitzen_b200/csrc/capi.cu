@@ -769,6 +769,11 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (strcmp(name, "early_bits") == 0) { c->optEarlyBits = value; return BLZ_OK; }
     if (strcmp(name, "vis_words") == 0) { c->optVisWords = value; return BLZ_OK; }
     if (strcmp(name, "draw_kernel") == 0) { c->optDrawKernel = value; return BLZ_OK; }
+    if (strcmp(name, "l2_fetch_granularity") == 0) {           // 32 / 64 / 128 bytes: device-wide hint (cudaLimitMaxL2FetchGranularity); the sparse early pass gathers 8-16 B per 200-400 B
+        CU_TRY(cudaSetDevice(c->device));
+        CU_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(value)));
+        return BLZ_OK;
+    }
     if (strcmp(name, "list_pipeline") == 0) { c->optListPipeline = value; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     if (strcmp(name, "stream_dynamic") == 0) { c->optStreamDynamic = value; return BLZ_OK; }

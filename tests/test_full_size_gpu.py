@@ -104,3 +104,53 @@ def test_shard_additivity_full_size(workload):
             got, _ = ctx.read_draws()
             parts.append(recs_u32(got))
     assert sha(np.concatenate(parts)) == sha(recs_u32(full)) and len(full) == ftot
+
+
+def test_instancing_and_cluster_path_full_size_against_oracle(workload):
+    """The other rows of the path at the bench size: indirect instancing (16.7 M objects, buckets sized from the oracle's counts, one bucket
+    deliberately too small) and the cluster path (expand -> 50 M dispatch records -> passthrough and bounding-sphere cull), byte for byte."""
+    from blitzen_b200 import capi
+    w, B = workload
+    threads = O.hardware_threads()
+    kw = dict(threads=threads, transform_id_base=w["transform_id_base"])
+    S = (w["objs"], w["transforms"], w["surfaces"], w["lods"])
+    view = w["view"]
+    nl = len(w["lods"])
+    # ---- instancing
+    li = w["lodInstances"].copy()
+    li["instanceOffset"] = np.arange(nl, dtype=np.uint32)
+    _, cnt, _ = O.cull_instanced(*S, li, np.ones(nl, dtype=np.uint32), view, **kw)
+    cap = np.maximum(cnt, 1).astype(np.uint32)
+    big = int(np.argmax(cnt))
+    cap[big] = cnt[big] // 2                                                    # overflowing bucket: ids beyond the capacity are dropped, the count is not
+    li["instanceOffset"] = np.concatenate([[0], np.cumsum(cap)[:-1]]).astype(np.uint32)
+    idx_e, cnt_e, cmds_e = O.cull_instanced(*S, li, cap, view, **kw)
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(*S, lod_instances=li, bucket_capacity=cap, transform_id_base=w["transform_id_base"])
+        ctx.set_view(view)
+        ctx.instanced()
+        cmds, total = ctx.read_draws(capi.REC_DX32)
+        idx, counters = ctx.read_instances(int(cap.sum()))
+    assert np.array_equal(counters["instanceCount"], cnt_e) and int(cnt_e.sum()) > 2_000_000
+    assert sha(recs_u32(cmds)) == sha(cmds_e) and total == len(cmds_e)
+    for l in range(nl):
+        o, c = int(li["instanceOffset"][l]), int(min(cnt_e[l], cap[l]))
+        assert sha(idx[o:o + c]) == sha(idx_e[o:o + c]), l
+        assert c < 2 or np.all(np.diff(idx[o:o + c].astype(np.int64)) > 0)       # ascending ids inside every bucket
+    # ---- cluster path
+    capacity = 64_000_000
+    d_exp, d_tot = O.cluster_expand(*S, view, capacity, **kw)
+    assert 40_000_000 < d_tot <= capacity
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(*S, clusters=w["clusters"], transform_id_base=w["transform_id_base"], cluster_dispatch_capacity=capacity, draw_capacity=capacity)
+        ctx.set_view(view)
+        ctx.cluster_expand()
+        got, gtot = ctx.read_cluster_dispatch()
+        assert gtot == d_tot and sha(got.view(np.uint32)) == sha(d_exp)
+        del got
+        for mode, omode in ((capi.CLUSTER_PASSTHROUGH, 0), (capi.CLUSTER_SPHERE, 1)):
+            exp, tot = O.cluster_cull(*S, w["clusters"], view, d_exp, omode, **kw)
+            ctx.cluster_cull(mode, capi.REC_VK24)
+            draws, dtot = ctx.read_draws(capi.REC_VK24)
+            assert dtot == tot and sha(recs_u32(draws)) == sha(exp), mode
+            del draws, exp
