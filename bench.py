@@ -286,6 +286,8 @@ def main():
 
     early_written, early_total = 0, 0
     ctx.early(capi.REC_VK24); early_written, early_total = ctx.read_count()
+    cs = ctx.consume_draws()          # what the indirect draw + vertex stage would read from this list, reduced on the device (csrc/consume.cu)
+    early_checksum = {"records": int(cs.records), "index_sum": int(cs.index_sum), "id_xor": "%016x" % int(cs.id_xor), "bad_object": int(cs.bad_object), "bad_lod": int(cs.bad_lod), "unsorted": int(cs.unsorted)}
     ctx.build_pyramid(variant); ctx.late(capi.REC_VK24, variant); late_written, late_total = ctx.read_count()
     o = ctx.outputs()
     pyr_texels = sum(max(1, o.pyramid_width >> i) * max(1, o.pyramid_height >> i) for i in range(o.pyramid_mips))
@@ -405,7 +407,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_frame": e2e_frame, "gpu_launches": int(launches),
                 "clocks": clocks,
-                "detail": {"visible_prev_frame": vis_prev, "early_draws": early_total, "late_draws": late_total,
+                "detail": {"visible_prev_frame": vis_prev, "early_draws": early_total, "late_draws": late_total, "early_list_checksum": early_checksum,
                            "kernel_ms": {"early": t_early, "pyramid": t_pyr, "late": t_late}}}
         print(json.dumps(line), flush=True)
     ctx.close()

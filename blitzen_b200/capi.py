@@ -43,6 +43,11 @@ class SceneDesc(C.Structure):
     ]
 
 
+class ConsumeSummary(C.Structure):
+    _fields_ = [("records", C.c_uint64), ("index_sum", C.c_uint64), ("instance_sum", C.c_uint64), ("id_sum", C.c_uint64), ("id_xor", C.c_uint64),
+                ("bad_object", C.c_uint32), ("bad_lod", C.c_uint32), ("unsorted", C.c_uint32), ("pad", C.c_uint32), ("lod_hist", C.c_uint32 * 256)]
+
+
 class Outputs(C.Structure):
     _fields_ = [
         ("draws", C.c_void_p), ("draw_count", C.c_void_p), ("visibility", C.c_void_p),
@@ -65,7 +70,7 @@ ABI_SYMBOLS = [
     "blz_cull_set_cluster_dispatch", "blz_cull_get_outputs", "blz_cull_read_draws", "blz_cull_read_count",
     "blz_cull_read_visibility", "blz_cull_read_cluster_dispatch", "blz_cull_read_instances", "blz_cull_read_pyramid",
     "blz_cull_gather_export", "blz_cull_gather_import", "blz_cull_gather_configure", "blz_cull_gather_push", "blz_cull_gather_push_async", "blz_cull_gather_join",
-    "blz_cull_gather_read", "blz_cull_gather_outputs", "blz_cull_launch_count", "blz_cull_set_option",
+    "blz_cull_gather_read", "blz_cull_gather_outputs", "blz_cull_consume_draws", "blz_cull_consume_instances", "blz_cull_launch_count", "blz_cull_set_option",
 ]
 
 _lib = None
@@ -99,6 +104,7 @@ def load_library():
         "blz_cull_gather_export": [vp, u64, i, vp], "blz_cull_gather_import": [vp, vp, i, i],
         "blz_cull_gather_configure": [vp, u64, i], "blz_cull_gather_push": [vp, u32], "blz_cull_gather_push_async": [vp, u32], "blz_cull_gather_join": [vp],
         "blz_cull_gather_read": [vp, u32, vp, u64, vp], "blz_cull_gather_outputs": [vp, C.POINTER(vp), C.POINTER(vp)],
+        "blz_cull_consume_draws": [vp, i, i, vp], "blz_cull_consume_instances": [vp, i, vp],
         "blz_cull_launch_count": [vp, C.POINTER(u64)], "blz_cull_set_option": [vp, C.c_char_p, C.c_int64],
     }
     for name, args in sig.items():
@@ -337,6 +343,17 @@ class CullContext:
         if n:
             self._check(self._lib.blz_cull_gather_read(self._h, int(epoch), _ptr(out), n, _ptr(counts)))
         return out, counts
+
+    # ---- draw-list consumer ------------------------------------------------------------------------------------------
+    def consume_draws(self, list_id=LIST_OPAQUE, kind=0):
+        out = ConsumeSummary()
+        self._check(self._lib.blz_cull_consume_draws(self._h, list_id, kind, C.byref(out)))
+        return out
+
+    def consume_instances(self, list_id=LIST_OPAQUE):
+        out = ConsumeSummary()
+        self._check(self._lib.blz_cull_consume_instances(self._h, list_id, C.byref(out)))
+        return out
 
     # ---- instrumentation -------------------------------------------------------------------------------------------
     def launch_count(self):

@@ -178,6 +178,18 @@ int blz_cull_read_cluster_dispatch(blz_cull_ctx* ctx, void* records_host, uint64
 int blz_cull_read_instances(blz_cull_ctx* ctx, uint32_t* instance_indices_host, uint64_t capacity, void* lod_instance_counters_host /* LodInstanceCounter[lod_count] */);
 int blz_cull_read_pyramid(blz_cull_ctx* ctx, float* pyramid_host, uint64_t capacity_texels, uint32_t* out_whm /* [3] */, uint32_t* out_offsets /* [16] */);
 
+/* ---- draw-list consumer (new): replays on the device what the indirect draw + vertex stage read from the outputs
+ * (records at stride 24 / 32, vulkanDraw.cpp:470-471; draws[gl_DrawID].objectId -> RenderObject -> surface / LOD table,
+ * MainObjectShader.vert.glsl:26; instIndices[objId + SV_InstanceID], opaqueDrawInst.vs.hlsl:11) and reduces them to a checksum.
+ * Synchronising.  kind 0 = object draws (each {indexCount, firstIndex} must be a LOD of the object's surface), 1 = cluster draws. */
+typedef struct blz_consume_summary {
+    uint64_t records, index_sum, instance_sum, id_sum, id_xor;   /* id_xor: xor of objectId * 0x9E3779B97F4A7C15 */
+    uint32_t bad_object, bad_lod, unsorted, pad;
+    uint32_t lod_hist[256];
+} blz_consume_summary;
+int blz_cull_consume_draws(blz_cull_ctx* ctx, int list, int kind, blz_consume_summary* out_host);
+int blz_cull_consume_instances(blz_cull_ctx* ctx, int list, blz_consume_summary* out_host);
+
 /* ---- multi-GPU draw-list gather (new; the reference is single-GPU) -------------------------------------------------
  * Each rank culls its shard; the per-rank lists are concatenated in shard order on the presenting rank.
  * Peer buffers are exchanged as CUDA IPC handles by the host layer (blitzen_b200/dist.py, torch.distributed).
