@@ -130,6 +130,7 @@ struct PyramidBuildParams {
     uint32_t tileLevels;               // levels produced inside the tile stage (<= 6)
     uint32_t boxW, boxH;               // input box staged per tile (texels)
     int variant;
+    uint32_t smemFloats;               // dynamic shared memory of a CTA, in floats (set by the launcher: the tail reuses it)
 };
 cudaError_t launch_pyramid_build(const PyramidBuildParams& p, const void* tensorMap /* CUtensorMap* on host or null */, cudaStream_t stream);
 size_t pyramid_smem_bytes(const PyramidBuildParams& p);

@@ -64,18 +64,23 @@ __device__ __forceinline__ float ld_cg_f32(const float* p)
     return v;
 }
 
-// generic per-level step from global memory (tail levels): mirrors oracle_build_pyramid
-template <int VARIANT>
-__device__ __forceinline__ float tail_texel(const float* src, uint32_t sw, uint32_t sh, uint32_t x, uint32_t y, uint32_t lw, uint32_t lh)
+// generic per-level step (tail levels): mirrors oracle_build_pyramid; `fetch(i, j)` returns texel (i, j) of the previous level
+template <int VARIANT, class Fetch>
+__device__ __forceinline__ float tail_texel_from(Fetch&& fetch, uint32_t sw, uint32_t sh, uint32_t x, uint32_t y, uint32_t lw, uint32_t lh)
 {
     if (VARIANT == HIZ_VK) {
         float s = fdiv(fadd(float(x), 0.5f), float(lw)), t = fdiv(fadd(float(y), 0.5f), float(lh));
-        return sample_min_linear([&](uint32_t i, uint32_t j) { return ld_cg_f32(src + size_t(j) * sw + i); }, sw, sh, s, t);
+        return sample_min_linear(fetch, sw, sh, s, t);
     } else {
-        auto ld = [&](uint32_t xx, uint32_t yy) { return (xx < sw && yy < sh) ? ld_cg_f32(src + size_t(yy) * sw + xx) : 0.0f; };
+        auto ld = [&](uint32_t xx, uint32_t yy) { return (xx < sw && yy < sh) ? fetch(xx, yy) : 0.0f; };
         float r = ld(2 * x, 2 * y), g = ld(2 * x + 1, 2 * y), b = ld(2 * x, 2 * y + 1), a = ld(2 * x + 1, 2 * y + 1);
         return min_keep(r, min_keep(g, min_keep(b, a)));
     }
+}
+template <int VARIANT>
+__device__ __forceinline__ float tail_texel(const float* src, uint32_t sw, uint32_t sh, uint32_t x, uint32_t y, uint32_t lw, uint32_t lh)
+{
+    return tail_texel_from<VARIANT>([&](uint32_t i, uint32_t j) { return ld_cg_f32(src + size_t(j) * sw + i); }, sw, sh, x, y, lw, lh);
 }
 
 template <int VARIANT, bool USE_TMA>
@@ -172,6 +177,36 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_kernel(const __grid_const
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // The tail is serial (one CTA, one level after the other): profiles/r01m_pyramid_raw.txt showed the SMs active for only half of the
+    // kernel's 19 us -- every tail level paid an L2 round trip per texel fetch plus a fence.  When the first tail level's source fits the
+    // shared memory this CTA already owns (32 x 32 texels at 1080p, 64 x 64 at 4K), it is loaded ONCE and the remaining levels are reduced
+    // there, ping-pong between two shared buffers, with the same arithmetic; otherwise the levels are stepped through global memory.
+    {
+        const uint32_t k0 = p.tileLevels;
+        const uint32_t sw0 = umax(1u, p.width >> (k0 - 1)), sh0 = umax(1u, p.height >> (k0 - 1));
+        const uint32_t lw0 = umax(1u, p.width >> k0), lh0 = umax(1u, p.height >> k0);
+        if (size_t(sw0) * sh0 + size_t(lw0) * lh0 <= p.smemFloats) {
+            float* a = reinterpret_cast<float*>(smem_raw);                  // previous level
+            float* b = a + size_t(sw0) * sh0;                               // current level (never larger than lw0 x lh0)
+            const float* src0 = p.out + p.offset[k0 - 1];
+            for (uint32_t idx = tid; idx < sw0 * sh0; idx += kPyrThreads) a[idx] = ld_cg_f32(src0 + idx);
+            __syncthreads();
+            for (uint32_t k = k0; k < p.mips; ++k) {
+                const uint32_t lw = umax(1u, p.width >> k), lh = umax(1u, p.height >> k);
+                const uint32_t sw = umax(1u, p.width >> (k - 1)), sh = umax(1u, p.height >> (k - 1));
+                float* dst = p.out + p.offset[k];
+                for (uint32_t idx = tid; idx < lw * lh; idx += kPyrThreads) {
+                    const uint32_t x = idx % lw, y = idx / lw;
+                    const float d = tail_texel_from<VARIANT>([&](uint32_t i, uint32_t j) { return a[size_t(j) * sw + i]; }, sw, sh, x, y, lw, lh);
+                    b[idx] = d;
+                    dst[idx] = d;
+                }
+                __syncthreads();
+                float* t = a; a = b; b = t;                                  // the old source (>= 4x larger) becomes the next destination
+            }
+            return;
+        }
+    }
     for (uint32_t k = p.tileLevels; k < p.mips; ++k) {
         const uint32_t lw = umax(1u, p.width >> k), lh = umax(1u, p.height >> k);
         const uint32_t sw = umax(1u, p.width >> (k - 1)), sh = umax(1u, p.height >> (k - 1));
@@ -199,6 +234,8 @@ size_t pyramid_smem_bytes(const PyramidBuildParams& p)
 cudaError_t launch_pyramid_build(const PyramidBuildParams& p, const void* tensorMap, cudaStream_t stream)
 {
     const size_t smem = pyramid_smem_bytes(p);
+    PyramidBuildParams q = p;
+    q.smemFloats = uint32_t(smem / sizeof(float));
     dim3 grid(p.tilesX, p.tilesY), block(kPyrThreads);
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
@@ -208,7 +245,7 @@ cudaError_t launch_pyramid_build(const PyramidBuildParams& p, const void* tensor
     else kernel = tensorMap ? pyramid_kernel<HIZ_DX, true> : pyramid_kernel<HIZ_DX, false>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    kernel<<<grid, block, smem, stream>>>(p, map);
+    kernel<<<grid, block, smem, stream>>>(q, map);
     return cudaGetLastError();
 }
 
