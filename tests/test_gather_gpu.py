@@ -1,0 +1,64 @@
+"""Draw-list gather on ONE GPU (world = 1: the presenter pushes into its own buffer): exercises the C-ABI gather entry points, the
+asynchronous push (side stream, double-buffered draw lists, two-half gather buffer) and the stream-ordered join inside the normal GPU
+suite; the multi-rank form is scripts/verify_gather.py (torchrun, 2/4/8 GPUs)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import view_at
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi(built):
+    from blitzen_b200 import capi
+    return capi
+
+
+def recs_u32(rec):
+    return rec.view(np.uint32).reshape(len(rec), rec.dtype.itemsize // 4)
+
+
+def test_gather_sync_and_async_single_rank(capi, small_scene):
+    sc = small_scene
+    n = len(sc["objs"])
+    view = view_at(position=(380, 380, 380), z_far=2000.0)
+    from blitzen_b200 import scene
+    depth = scene.synthetic_depth(640, 360, n_rects=40, z_min=20.0, z_max=300.0, seed=5)
+    S = (sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view)
+    vis0 = np.zeros(n, dtype=np.uint32)
+    l0, _, vis1 = O.cull(*S, O.PASS_LATE, pyramid=O.cleared_pyramid(640, 360, O.HIZ_VK), vis=vis0)
+    pyr = O.build_pyramid(depth, O.HIZ_VK)
+    e1, _, _ = O.cull(*S, O.PASS_EARLY, vis=vis1)
+    l1, _, vis2 = O.cull(*S, O.PASS_LATE, pyramid=pyr, vis=vis1)
+    e2, _, _ = O.cull(*S, O.PASS_EARLY, vis=vis2)
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"])
+        ctx.set_view(view); ctx.set_depth(depth)
+        blob = ctx.gather_export(n, capi.REC_VK24)
+        ctx.gather_import(None, 0, 1, n, capi.REC_VK24)
+        # frame 0, synchronous push
+        ctx.clear_pyramid(capi.HIZ_VK, 640, 360)
+        ctx.late(); ctx.gather_push(1)
+        got, counts = ctx.gather_read(1, 1)
+        assert counts[0] == len(l0) and np.array_equal(recs_u32(got), l0)
+        # frame 1, asynchronous pushes: both lists of the frame are intact on the presenter afterwards (two halves of the gather buffer)
+        ctx.early(); ctx.gather_push_async(2)
+        ctx.build_pyramid(capi.HIZ_VK)
+        ctx.late(); ctx.gather_push_async(3)
+        ctx.gather_join(); ctx.synchronize()
+        gotE, cE = ctx.gather_read(2, 1)
+        gotL, cL = ctx.gather_read(3, 1)
+        assert cE[0] == len(e1) and np.array_equal(recs_u32(gotE), e1)
+        assert cL[0] == len(l1) and np.array_equal(recs_u32(gotL), l1)
+        assert np.array_equal(ctx.read_visibility(), vis2)
+        # frame 2: the draw buffers have flipped twice; passes and pushes keep working, read_draws sees the pass that ran last
+        ctx.early()
+        last, _ = ctx.read_draws()
+        assert np.array_equal(recs_u32(last), e2)
+        ctx.gather_push_async(4)
+        ctx.late(); ctx.gather_push_async(5)
+        ctx.gather_join()
+        gotE, _ = ctx.gather_read(4, 1)
+        assert np.array_equal(recs_u32(gotE), e2)
