@@ -33,6 +33,8 @@ struct blz_cull_ctx {
     bool visListValid = false;                // true while visibility[] has not been written by anything but that late pass
     uint32_t* dispatch = nullptr; uint64_t dispatchCap = 0;
     uint32_t* instIdx = nullptr; uint64_t instCap = 0;
+    uint32_t* visTotalHost = nullptr;         // pinned: number of previously-visible objects the last COMPLETED early pass saw (lags by a frame; a hint only)
+    bool earlyDense = false;                  // early pass currently runs the dense (streaming) kernel instead of the sparse pipelined one
     uint2* survList = nullptr; size_t capSurvList = 0;       // {objectId, absolute LOD id} of the frustum survivors (instancing / cluster expand, cull_list.cu)
     uint32_t* listScratch = nullptr; size_t capListScratch = 0;   // per-tile histograms / record counts of the survivor-list kernels
     blz::ScanCtl* ctl = nullptr;
@@ -53,6 +55,7 @@ struct blz_cull_ctx {
     int64_t optVisWords = 0;                  // 1: the streaming late pass also writes the u32-per-object visibility buffer every frame (else on demand)
     int64_t optDrawKernel = 1;                // 0 = pipelined kernel (cull_draw.cu), 1 = streaming kernel (cull_stream.cu)
     int64_t optStreamDynamic = 1;             // streaming kernel: atomic-ticket tile order (1) or static round-robin (0)
+    int64_t optEarlyAuto = 1;                 // early_mode 3: switch to the streaming kernel while more than ~20 % of the objects were visible last frame
     int64_t optListPipeline = 1;              // instancing / cluster expand: 1 = streaming frustum pass -> survivor list -> cull_list.cu, 0 = one-shot kernels (cull_inst_cluster.cu)
     int64_t optStreamCfg = 2;                 // CTA shape of the streaming kernel (see launch_pass in cull_stream.cu)
     uint32_t lastRecWords = 6;                // record width (u32 words) of the pass that last wrote `draws`

@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(kEsThreads, BITS ? 3 : 4) early_stream_kernel(
     uint2 ob = make_uint2(0u, 0u); uint32_t locB = 0u;        // B -> C
     float4 ps = make_float4(0.f, 0.f, 0.f, 1.f), qt = make_float4(0.f, 0.f, 0.f, 1.f); uint32_t sidC = 0u, locC = 0u;   // C -> D
     uint32_t tileEmitted = 0u;                                // descriptors staged so far for the tile in D
+    uint32_t candSum = 0u;                                    // thread 0: previously-visible objects of the tiles this CTA compacted (feedback for the C-ABI layer's choice of kernel)
     // finished tiles waiting for their prefix: records go out two iterations after the aggregate was published
     uint32_t f1Tile = kEsNone, f1Total = 0u, f1Slot = 0u, f2Tile = kEsNone, f2Total = 0u, f2Slot = 0u;
     uint32_t cum = 0u, nextRead = 0u;
@@ -589,6 +590,7 @@ __global__ void __launch_bounds__(kEsThreads, BITS ? 3 : 4) early_stream_kernel(
             if (aTile != kEsNone) {
                 // the tile just compacted becomes current as soon as the previous one has handed its last batch to B (this iteration)
                 curTile = aTile; curSeq = nextSeq; curCand = aCand; curNext = 0u;
+                candSum += aCand;
                 ++nextSeq;
                 if (BITS) {                                  // its successor's ticket became visible behind barrier (2): the mask word goes out now
                     const uint32_t nt = tile_of(nextSeq);
@@ -601,9 +603,12 @@ __global__ void __launch_bounds__(kEsThreads, BITS ? 3 : 4) early_stream_kernel(
 
     if (p.n == 0u && blockIdx.x == 0 && tid == 0) { p.counts[0] = 0u; p.counts[1] = 0u; }
     if (tid == 0) {
+        if (p.visTotal != nullptr && candSum != 0u) atomicAdd(p.visTotal, candSum);
         __threadfence();
         const uint32_t prev = atomicAdd(&p.ctl->done, 1u);
         if (prev == gridDim.x - 1u) {
+            // last CTA out: the total goes straight to the host-mapped word (one posted write, no memset / memcpy on the stream), accumulator re-armed
+            if (p.visTotal != nullptr) { const uint32_t tot = atomicExch(p.visTotal, 0u); *reinterpret_cast<volatile uint32_t*>(p.visTotalOut) = tot; }
             uint32_t e = (epoch + 1u) & 0x3FFFFFFFu;
             p.ctl->epoch = e ? e : 1u;
             p.ctl->ticket = 0u;
@@ -652,6 +657,23 @@ __global__ void unpack_vis_bits_kernel(const uint32_t* __restrict__ bits, uint32
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) vis[i] = (__ldg(bits + (i >> 5)) >> (i & 31u)) & 1u;
+}
+
+// population of the 1-bit visibility mask (2 MB for 16.7 M objects): only launched next to the DENSE early pass, whose kernel does not count
+__global__ void popc_vis_bits_kernel(const uint32_t* __restrict__ bits, uint32_t words, uint32_t* __restrict__ total)
+{
+    uint32_t acc = 0u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) acc += uint32_t(__popc(__ldg(bits + i)));
+    acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+    if ((threadIdx.x & 31u) == 0u && acc != 0u) atomicAdd(total, acc);
+}
+
+cudaError_t launch_popc_vis_bits(const uint32_t* bits, uint32_t n, uint32_t* total, cudaStream_t stream)
+{
+    const uint32_t words = (n + 31u) / 32u;
+    if (words == 0u) return cudaSuccess;
+    popc_vis_bits_kernel<<<148, 256, 0, stream>>>(bits, words, total);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_unpack_vis_bits(const uint32_t* bits, uint32_t* vis, uint32_t n, cudaStream_t stream)

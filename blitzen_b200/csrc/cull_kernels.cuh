@@ -26,6 +26,8 @@ struct DrawCullParams {
     uint32_t* counts;                // [0] = written (clamped to capacity), [1] = total
     uint32_t* visList;               // late pass: ascending LOCAL indices of the objects it found visible (may be null); early-list pass: its input
     uint32_t* visCount;              // device word holding the length of visList
+    uint32_t* visTotal;              // pipelined early pass: += number of previously-visible objects it walked (may be null) ...
+    uint32_t* visTotalOut;           // ... and the last CTA out stores the total here (host-mapped pinned word) and zeroes the accumulator
     uint32_t* visBits;               // 1 bit per object (word i = objects 32i..32i+31): written by the streaming late pass, source of the pipelined early pass (may be null)
     // scan state
     ScanCtl* ctl;
@@ -113,6 +115,7 @@ cudaError_t launch_stream_cull(const DrawCullParams& p, int pass, int hiz, int c
 cudaError_t launch_early_stream(const DrawCullParams& p, int numSMs, cudaStream_t stream);   // cull_early.cu: pipelined early pass (default)
 cudaError_t launch_pack_vis_bits(const uint32_t* vis, uint32_t* bits, uint32_t n, cudaStream_t stream);   // cull_early.cu
 cudaError_t launch_unpack_vis_bits(const uint32_t* bits, uint32_t* vis, uint32_t n, cudaStream_t stream); // cull_early.cu
+cudaError_t launch_popc_vis_bits(const uint32_t* bits, uint32_t n, uint32_t* total, cudaStream_t stream);   // cull_early.cu
 cudaError_t launch_early_sparse(const DrawCullParams& p, cudaStream_t stream);
 cudaError_t launch_early_list(const DrawCullParams& p, int numSMs, cudaStream_t stream);   // cull_early.cu: PASS_EARLY over the late pass's visible list   // cull_early.cu: PASS_EARLY for mostly-invisible scenes
 cudaError_t launch_instance_cull(const InstanceCullParams& p, int numSMs, cudaStream_t stream);

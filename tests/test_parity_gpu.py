@@ -348,3 +348,25 @@ def test_against_reference_shader_outputs(capi, built, tables):
             got, _ = ctx.read_draws()
             assert np.array_equal(recs_u32(got), g[f"head_late_{vn}"]), vn
             assert np.array_equal(ctx.read_visibility(), g[f"head_late_vis_{vn}"]), vn
+
+
+def test_early_pass_density_switch(capi, medium_scene):
+    """The early pass switches between its sparse (pipelined) and dense (streaming) kernels on the density it observed a frame earlier
+    (asynchronous device -> pinned-host feedback): the list is the oracle's whichever kernel runs, through both transitions."""
+    sc = medium_scene
+    n = len(sc["objs"])
+    view = view_at(position=(950, 950, 950), z_far=3000.0)
+    S = (sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view)
+    rng = np.random.default_rng(3)
+    dense = np.ones(n, dtype=np.uint32)
+    sparse = (rng.random(n) < 0.03).astype(np.uint32)
+    exp_d, _, _ = O.cull(*S, O.PASS_EARLY, vis=dense)
+    exp_s, _, _ = O.cull(*S, O.PASS_EARLY, vis=sparse)
+    with make_ctx(capi, sc) as ctx:
+        ctx.set_view(view)
+        for vis, exp in ((dense, exp_d), (sparse, exp_s), (dense, exp_d)):
+            ctx.write_visibility(vis)
+            for _ in range(4):
+                ctx.early()
+                got, tot = ctx.read_draws()
+                assert tot == len(exp) and np.array_equal(recs_u32(got), exp)
