@@ -70,7 +70,7 @@ ABI_SYMBOLS = [
     "blz_cull_set_cluster_dispatch", "blz_cull_get_outputs", "blz_cull_read_draws", "blz_cull_read_count",
     "blz_cull_read_visibility", "blz_cull_read_cluster_dispatch", "blz_cull_read_instances", "blz_cull_read_pyramid",
     "blz_cull_gather_export", "blz_cull_gather_import", "blz_cull_gather_configure", "blz_cull_gather_push", "blz_cull_gather_push_async", "blz_cull_gather_join",
-    "blz_cull_gather_read", "blz_cull_gather_outputs", "blz_cull_consume_draws", "blz_cull_consume_instances", "blz_cull_launch_count", "blz_cull_set_option",
+    "blz_cull_gather_read", "blz_cull_gather_outputs", "blz_cull_instances_export", "blz_cull_instances_import", "blz_cull_instances_push", "blz_cull_instances_counts", "blz_cull_consume_draws", "blz_cull_consume_instances", "blz_cull_launch_count", "blz_cull_set_option",
 ]
 
 _lib = None
@@ -104,6 +104,7 @@ def load_library():
         "blz_cull_gather_export": [vp, u64, i, vp], "blz_cull_gather_import": [vp, vp, i, i],
         "blz_cull_gather_configure": [vp, u64, i], "blz_cull_gather_push": [vp, u32], "blz_cull_gather_push_async": [vp, u32], "blz_cull_gather_join": [vp],
         "blz_cull_gather_read": [vp, u32, vp, u64, vp], "blz_cull_gather_outputs": [vp, C.POINTER(vp), C.POINTER(vp)],
+        "blz_cull_instances_export": [vp, vp], "blz_cull_instances_import": [vp, vp, i, i], "blz_cull_instances_push": [vp, vp, vp, vp], "blz_cull_instances_counts": [vp, vp],
         "blz_cull_consume_draws": [vp, i, i, vp], "blz_cull_consume_instances": [vp, i, vp],
         "blz_cull_launch_count": [vp, C.POINTER(u64)], "blz_cull_set_option": [vp, C.c_char_p, C.c_int64],
     }
@@ -343,6 +344,21 @@ class CullContext:
         if n:
             self._check(self._lib.blz_cull_gather_read(self._h, int(epoch), _ptr(out), n, _ptr(counts)))
         return out, counts
+
+    def instances_export(self):
+        blob = np.zeros(64, dtype=np.uint8)
+        self._check(self._lib.blz_cull_instances_export(self._h, _ptr(blob)))
+        return blob
+
+    def instances_import(self, blob, rank, world):
+        b = None if blob is None else np.ascontiguousarray(blob, dtype=np.uint8)
+        self._check(self._lib.blz_cull_instances_import(self._h, _ptr(b), rank, world))
+
+    def instances_counts(self, dst_device_ptr):
+        self._check(self._lib.blz_cull_instances_counts(self._h, C.c_void_p(dst_device_ptr)))
+
+    def instances_push(self, all_counts_ptr, global_offset_ptr, global_cap_ptr):
+        self._check(self._lib.blz_cull_instances_push(self._h, C.c_void_p(all_counts_ptr), C.c_void_p(global_offset_ptr), C.c_void_p(global_cap_ptr)))
 
     # ---- draw-list consumer ------------------------------------------------------------------------------------------
     def consume_draws(self, list_id=LIST_OPAQUE, kind=0):

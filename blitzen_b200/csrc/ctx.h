@@ -63,6 +63,7 @@ struct blz_cull_ctx {
     uint32_t* gatherBuf = nullptr; uint64_t gatherCap = 0; uint32_t gatherRecWords = 6; uint64_t* gatherFlags = nullptr; bool gatherOwner = false;
     uint32_t* gatherDst = nullptr; uint64_t* gatherDstFlags = nullptr; int rank = 0, world = 1; bool gatherImported = false, gatherPeerMapped = false;
     uint32_t* gatherDone = nullptr;
+    uint32_t* instDst = nullptr; bool instDstMapped = false;   // presenter's instance index buffer (instance-list gather)
     // asynchronous push: the list just pushed stays readable in `drawsAlt` while the next pass writes `draws` (blz_cull_gather_push_async)
     uint32_t* drawsAlt = nullptr; uint32_t lastRecWordsAlt = 6; int drawSlot = 0;
     cudaStream_t gatherStream = nullptr; cudaEvent_t evCull = nullptr, evPush[2] = { nullptr, nullptr }; bool evPushValid[2] = { false, false };

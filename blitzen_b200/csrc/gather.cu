@@ -8,6 +8,7 @@
 // No NCCL call and no host round trip on the data path; NCCL (torch.distributed) only carries the 128-byte IPC handle
 // blob at set-up time (blitzen_b200/dist.py).
 #include "ctx.h"
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 
@@ -100,6 +101,34 @@ __global__ void gather_wait_kernel(const uint64_t* flags, uint32_t world, uint32
     if (r < world) { while (int32_t(uint32_t(ld_acquire_sys_u64(flags + kDoneRow * kFlagStride + r)) - epoch) < 0) { } }
 }
 
+// Instance-list gather (indirect instancing, objects sharded by contiguous ranges): the bucket of LOD l on the presenter is the concatenation of
+// the ranks' buckets in rank order (= ascending objectId).  The per-rank per-LOD counts arrive by an NCCL all-gather issued by the host layer on
+// the same stream (all-gather of the counts, exclusive scan, variable-length gather); this kernel does the scan (<= 8 ranks) and the
+// peer stores.  grid.y = LOD.
+struct InstGatherParams {
+    const uint32_t* src; const LodInstanceCounter* local;     // this rank's buckets: instanceOffset (local layout) + instanceCount
+    const uint32_t* localCap;
+    const uint32_t* allCounts;                                // [world][lodCount] instanceCount of every rank (device)
+    const uint32_t* globalOffset; const uint32_t* globalCap;  // presenter's bucket layout
+    uint32_t* dst;                                            // presenter's instance index buffer (peer-mapped, or local on the presenter)
+    uint32_t lodCount, rank, world;
+};
+
+__global__ void __launch_bounds__(kGatherThreads) gather_instances_kernel(const InstGatherParams p)
+{
+    const uint32_t l = blockIdx.y;
+    if (l >= p.lodCount) return;
+    uint32_t base = 0u;
+    for (uint32_t r = 0; r < p.rank; ++r) base += p.allCounts[r * p.lodCount + l];
+    uint32_t cnt = p.allCounts[p.rank * p.lodCount + l];
+    if (cnt > p.localCap[l]) cnt = p.localCap[l];
+    const uint32_t room = base < p.globalCap[l] ? p.globalCap[l] - base : 0u;
+    if (cnt > room) cnt = room;
+    const uint32_t* s = p.src + p.local[l].instanceOffset;
+    uint32_t* d = p.dst + size_t(p.globalOffset[l]) + base;
+    for (uint32_t i = blockIdx.x * kGatherThreads + threadIdx.x; i < cnt; i += gridDim.x * kGatherThreads) d[i] = s[i];
+}
+
 } // namespace
 
 void gather_release(blz_cull_ctx* c)
@@ -109,6 +138,8 @@ void gather_release(blz_cull_ctx* c)
         if (c->gatherDstFlags) cudaIpcCloseMemHandle(c->gatherDstFlags);
     }
     if (c->gatherOwner) { if (c->gatherBuf) cudaFree(c->gatherBuf); if (c->gatherFlags) cudaFree(c->gatherFlags); }
+    if (c->instDstMapped && c->instDst) cudaIpcCloseMemHandle(c->instDst);
+    c->instDst = nullptr; c->instDstMapped = false;
     if (c->gatherDone) cudaFree(c->gatherDone);
     if (c->gatherStream) { cudaStreamSynchronize(c->gatherStream); cudaStreamDestroy(c->gatherStream); cudaEventDestroy(c->evCull); cudaEventDestroy(c->evPush[0]); cudaEventDestroy(c->evPush[1]); c->gatherStream = nullptr; c->evPushValid[0] = c->evPushValid[1] = false; }
     c->gatherBuf = nullptr; c->gatherFlags = nullptr; c->gatherDst = nullptr; c->gatherDstFlags = nullptr; c->gatherDone = nullptr;
@@ -264,6 +295,60 @@ int blz_cull_gather_read(blz_cull_ctx* c, uint32_t epoch, void* recordsHost, uin
             CU_TRY(cudaStreamSynchronize(c->stream));
         }
     }
+    return BLZ_OK;
+}
+
+// ---- instance-list gather -------------------------------------------------------------------------------------------------------
+int blz_cull_instances_export(blz_cull_ctx* c, void* outBlob64)
+{
+    if (!c || !outBlob64 || !c->instIdx) return fail(BLZ_ERR_INVALID, "scene was uploaded without lod_instances");
+    CU_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, c->instIdx));
+    memcpy(outBlob64, &h, 64);
+    return BLZ_OK;
+}
+
+int blz_cull_instances_import(blz_cull_ctx* c, const void* presenterBlob64, int rank, int world)
+{
+    if (!c || rank < 0 || world < 1 || rank >= world) return fail(BLZ_ERR_INVALID, "bad rank/world %d/%d", rank, world);
+    CU_TRY(cudaSetDevice(c->device));
+    if (c->instDstMapped && c->instDst) { cudaIpcCloseMemHandle(c->instDst); c->instDst = nullptr; c->instDstMapped = false; }
+    c->rank = rank; c->world = world;
+    if (!presenterBlob64) { c->instDst = c->instIdx; c->instDstMapped = false; return BLZ_OK; }      // the presenter itself
+    cudaIpcMemHandle_t h;
+    memcpy(&h, presenterBlob64, 64);
+    void* a = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&a, h, cudaIpcMemLazyEnablePeerAccess));
+    c->instDst = static_cast<uint32_t*>(a); c->instDstMapped = true;
+    return BLZ_OK;
+}
+
+// all_counts_device: [world][lod_count] instanceCount of every rank; global_offset / global_cap: the presenter's bucket layout (device arrays).
+// On the presenter the destination IS its own instance buffer, whose local buckets would be overwritten while they are read: the presenter
+// must be rank 0 (its data stays where it is: global offset == local offset, base 0).
+int blz_cull_instances_push(blz_cull_ctx* c, const uint32_t* allCounts, const uint32_t* globalOffset, const uint32_t* globalCap)
+{
+    if (!c || !c->instDst || !c->lodInst || !allCounts || !globalOffset || !globalCap) return fail(BLZ_ERR_INVALID, "instance gather not set up");
+    CU_TRY(cudaSetDevice(c->device));
+    if (!c->instDstMapped) return BLZ_OK;                     // rank 0: already in place
+    InstGatherParams p{};
+    p.src = c->instIdx; p.local = c->lodInst; p.localCap = c->bucketCap; p.allCounts = allCounts; p.globalOffset = globalOffset; p.globalCap = globalCap;
+    p.dst = c->instDst; p.lodCount = c->nLods; p.rank = uint32_t(c->rank); p.world = uint32_t(c->world);
+    dim3 grid(16u, c->nLods);
+    gather_instances_kernel<<<grid, kGatherThreads, 0, c->stream>>>(p);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return BLZ_OK;
+}
+
+// the per-LOD instanceCount words of the last instancing pass, packed into a caller-owned DEVICE array (stream-ordered): what the host layer all-gathers
+int blz_cull_instances_counts(blz_cull_ctx* c, uint32_t* dstDevice)
+{
+    if (!c || !c->lodInst || !dstDevice) return fail(BLZ_ERR_INVALID, "scene was uploaded without lod_instances");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaMemcpy2DAsync(dstDevice, sizeof(uint32_t), reinterpret_cast<const unsigned char*>(c->lodInst) + offsetof(LodInstanceCounter, instanceCount),
+                             sizeof(LodInstanceCounter), sizeof(uint32_t), c->nLods, cudaMemcpyDeviceToDevice, c->stream));
     return BLZ_OK;
 }
 

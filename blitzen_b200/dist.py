@@ -56,3 +56,37 @@ class DrawListGather:
         if self.rank != self.presenter:
             raise RuntimeError("only the presenting rank reads the gathered list")
         return self.ctx.gather_read(epoch, self.world, self.fmt)
+
+
+class InstanceListGather:
+    """Indirect instancing over object shards: the per-LOD buckets of the ranks are concatenated in rank order on rank 0 (the presenter, whose
+    own buckets start the global ones).  The only collective is an NCCL all-gather of the per-rank per-LOD counts (lod_count words per rank),
+    issued on the context's stream; the instance ids travel by peer stores (blz_cull_instances_push).  `global_offset` / `global_cap`: bucket
+    layout of the presenter's instance buffer (numpy uint32 [lod_count]); every rank's LOCAL layout must start bucket l at global_offset[l] on
+    rank 0 (it is the same buffer there)."""
+
+    def __init__(self, ctx, rank, world, n_lods, global_offset, global_cap, stream):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world, self.n_lods, self.stream = ctx, rank, world, n_lods, stream
+        t = torch.from_numpy(ctx.instances_export().copy()).cuda() if rank == 0 else torch.zeros(64, dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, src=0)
+        ctx.instances_import(None if rank == 0 else t.cpu().numpy(), rank, world)
+        self.mine = torch.zeros(n_lods, dtype=torch.int32, device="cuda")
+        self.all = torch.zeros(world * n_lods, dtype=torch.int32, device="cuda")
+        self.goff = torch.from_numpy(np.ascontiguousarray(global_offset, dtype=np.uint32).view(np.int32)).cuda()
+        self.gcap = torch.from_numpy(np.ascontiguousarray(global_cap, dtype=np.uint32).view(np.int32)).cuda()
+        dist.barrier()
+
+    def push(self):
+        """After ctx.instanced() on every rank; stream-ordered, no host synchronisation."""
+        import torch
+        import torch.distributed as dist
+        with torch.cuda.stream(self.stream):
+            self.ctx.instances_counts(self.mine.data_ptr())
+            dist.all_gather_into_tensor(self.all, self.mine)
+            self.ctx.instances_push(self.all.data_ptr(), self.goff.data_ptr(), self.gcap.data_ptr())
+
+    def totals(self):
+        """Per-LOD totals over all ranks (host; synchronises)."""
+        return self.all.view(self.world, self.n_lods).sum(dim=0).cpu().numpy().astype(np.uint32)

@@ -212,6 +212,13 @@ int blz_cull_gather_push(blz_cull_ctx* ctx, uint32_t epoch);
 int blz_cull_gather_push_async(blz_cull_ctx* ctx, uint32_t epoch);
 int blz_cull_gather_join(blz_cull_ctx* ctx);   /* main stream waits for the asynchronous pushes issued so far (stream-ordered) */
 int blz_cull_gather_read(blz_cull_ctx* ctx, uint32_t epoch, void* records_host, uint64_t capacity_records, uint32_t* out_counts /* world entries */);
+/* instance-list gather (indirect instancing, objects sharded by contiguous ranges; the presenter must be rank 0, whose buckets start the
+ * global ones): the host layer all-gathers the per-rank per-LOD instanceCount words (NCCL, same stream) and every other rank stores its
+ * buckets behind the lower ranks' into the presenter's instance index buffer over NVLink peer memory. */
+int blz_cull_instances_export(blz_cull_ctx* ctx, void* out_blob64);
+int blz_cull_instances_import(blz_cull_ctx* ctx, const void* presenter_blob64 /* NULL on the presenter */, int rank, int world);
+int blz_cull_instances_counts(blz_cull_ctx* ctx, uint32_t* dst_device /* lod_count words, stream-ordered */);
+int blz_cull_instances_push(blz_cull_ctx* ctx, const uint32_t* all_counts_device /* [world][lod_count] */, const uint32_t* global_offset_device, const uint32_t* global_cap_device);
 int blz_cull_gather_outputs(blz_cull_ctx* ctx, void** out_records_device, uint32_t** out_flags_device);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------------------ */
