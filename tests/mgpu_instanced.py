@@ -3,7 +3,7 @@
 buckets gathered on rank 0 (NCCL all-gather of the per-rank per-LOD counts + peer stores of the ids, blitzen_b200/dist.py InstanceListGather).
 First a verification run (3 M objects): rank 0's gathered buckets + totals == the oracle's for the whole scene; then the timed run.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 scripts/multi_instanced.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 tests/mgpu_instanced.py
 """
 import argparse
 import json

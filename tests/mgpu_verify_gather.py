@@ -2,7 +2,7 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU): every rank culls its contiguous shard, pushes its draw list
 into the presenting rank's buffer over NVLink peer memory (blz_cull_gather_push), and rank 0 compares the concatenated list
 with the oracle's list for the WHOLE scene: byte-identical, for a frustum pass and for a two-phase frame (early + late lists).
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/verify_gather.py"""
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_verify_gather.py"""
 import os
 import sys
 

@@ -1,6 +1,6 @@
 """Draw-list gather on ONE GPU (world = 1: the presenter pushes into its own buffer): exercises the C-ABI gather entry points, the
 asynchronous push (side stream, double-buffered draw lists, two-half gather buffer) and the stream-ordered join inside the normal GPU
-suite; the multi-rank form is scripts/verify_gather.py (torchrun, 2/4/8 GPUs)."""
+suite; the multi-rank form is tests/mgpu_verify_gather.py (torchrun, 2/4/8 GPUs)."""
 import numpy as np
 import pytest
 
