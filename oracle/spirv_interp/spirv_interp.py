@@ -9,6 +9,16 @@ Scope: exactly the instruction subset those eight shaders use (scalar / vector f
 control flow, function calls, storage / uniform / push-constant / physical-storage buffers with explicit layouts, one atomic,
 one sampled-image fetch, one storage-image write, seven GLSL.std.450 functions).  Anything else raises NotImplementedError.
 
+Round 2: the same machine also executes the reference's nine D3D12 compute shaders (HlslShaders/CS/*.hlsl compiled by the
+same bundled glslang with its HLSL front end, `-D -e csMain`, oracle/Makefile target `hlsl_spv`).  That adds OpSwitch (the
+front end's early-return structuring), OpUndef, OpVectorTimesMatrix + RowMajor cbuffer matrices, OpImageFetch
+(Texture2D.Load), OpImageTexelPointer (RWBuffer<uint> atomics), OpConvertFToU, shifts and UMax/UMin.  Three operations are
+undefined in SPIR-V for some operands and get the semantics the D3D shader instructions they were written for have
+(Direct3D 11.3 Functional Specification, the instruction set HLSL SM5/6 integer and conversion ops lower to):
+  ConvertFToU           `ftou`: round toward zero, NaN -> 0, negative -> 0, >= 2^32 -> 0xFFFFFFFF (saturating)
+  ShiftRight/LeftLogical `ushr` / `ishl`: the shift amount is the low 5 bits of the operand
+  ImageFetch            `ld`: any coordinate or mip level outside the resource returns 0 in every component
+
 Arithmetic rules: every floating-point instruction is one IEEE-754 binary32 operation, round-to-nearest, no
 contraction.  Where SPIR-V leaves the evaluation order open the order of the reference's own math library is used:
   OpMatrixTimesVector   r_i = ((m[0][i]*v0 + m[1][i]*v1) + m[2][i]*v2) + m[3][i]*v3   (BlitzenMathLibrary/blitMLTypes.h:184-193)
@@ -40,12 +50,14 @@ OP = dict(Name=5, MemberName=6, ExtInstImport=11, ExtInst=12, MemoryModel=14, En
           FOrdLessThanEqual=188, FOrdGreaterThanEqual=190, AtomicIAdd=234, Phi=245, LoopMerge=246, SelectionMerge=247, Label=248,
           Branch=249, BranchConditional=250, Return=253, ReturnValue=254, CopyLogical=400, Source=3, SourceExtension=4,
           String=7, Line=8, ModuleProcessed=330, ConvertUToPtr=120, ConvertPtrToU=117, ShiftRightLogical=194, ShiftLeftLogical=196,
-          BitwiseAnd=199, BitwiseOr=197)
+          BitwiseAnd=199, BitwiseOr=197, Undef=1, Switch=251, ImageFetch=95, ImageTexelPointer=60, VectorTimesMatrix=144,
+          Image=100)
 OPN = {v: k for k, v in OP.items()}
-DEC_BUILTIN, DEC_BINDING, DEC_DESCRIPTOR_SET, DEC_OFFSET, DEC_ARRAY_STRIDE, DEC_MATRIX_STRIDE = 11, 33, 34, 35, 6, 7
+DEC_BUILTIN, DEC_BINDING, DEC_DESCRIPTOR_SET, DEC_OFFSET, DEC_ARRAY_STRIDE, DEC_MATRIX_STRIDE, DEC_ROW_MAJOR = 11, 33, 34, 35, 6, 7, 4
 SC_UNIFORM, SC_INPUT, SC_FUNCTION, SC_PRIVATE, SC_PUSH, SC_STORAGE_BUFFER, SC_UNIFORM_CONSTANT, SC_PHYSICAL = 2, 1, 7, 6, 9, 12, 0, 5349
 BUILTIN_GLOBAL_INVOCATION_ID, BUILTIN_WORKGROUP_ID, BUILTIN_LOCAL_INVOCATION_ID, BUILTIN_NUM_WORKGROUPS = 28, 26, 27, 24
 GLSL_FABS, GLSL_FLOOR, GLSL_LOG2, GLSL_SQRT, GLSL_FMAX, GLSL_FMIN, GLSL_LENGTH, GLSL_CROSS = 4, 8, 30, 31, 40, 37, 66, 68
+GLSL_UMIN, GLSL_UMAX = 38, 41
 
 
 class Type:
@@ -80,6 +92,29 @@ class Sampler2D:
 class StorageImage2D:
     def __init__(self, array):
         self.array = array   # numpy float32 [h, w]
+
+
+class Texture2D:
+    """Texture2D<float4> read with .Load(uint3(x, y, mip)) (OpImageFetch): mips = list of float32 [h, w]; only .r is modelled.
+    D3D `ld` rule: a mip level or coordinate outside the resource returns 0."""
+
+    def __init__(self, mips):
+        self.mips = mips
+
+    def fetch(self, x, y, lod):
+        if not (0 <= lod < len(self.mips)):
+            return f32(0)
+        img = self.mips[lod]
+        if 0 <= x < img.shape[1] and 0 <= y < img.shape[0]:
+            return f32(img[y, x])
+        return f32(0)
+
+
+class TexelBufferU32:
+    """RWBuffer<uint> (a storage texel buffer, format R32ui): numpy uint8 bytes, one u32 per texel."""
+
+    def __init__(self, bytes_u8):
+        self.bytes = bytes_u8
 
 
 class Module:
@@ -138,7 +173,7 @@ class Module:
             elif name == "TypeMatrix":
                 self.types[a[0]] = Type("matrix", col=a[1], count=a[2])
             elif name == "TypeImage":
-                self.types[a[0]] = Type("image")
+                self.types[a[0]] = Type("image", dim=a[2], sampled=a[6])
             elif name == "TypeSampledImage":
                 self.types[a[0]] = Type("sampled_image")
             elif name == "TypeArray":
@@ -161,6 +196,8 @@ class Module:
                 self.consts[a[1]] = [self.consts[x] for x in a[2:]]
             elif name == "Variable":
                 self.variables[a[1]] = (a[0], a[2])
+            elif name == "Undef":
+                self.consts[a[1]] = self.default_value(a[0])
             elif name == "Function":
                 cur = {"id": a[1], "params": [], "code": [], "labels": {}}
                 self.functions[a[1]] = cur
@@ -197,6 +234,26 @@ class Module:
             return self.decor[tid][DEC_ARRAY_STRIDE] * self.consts[t.length_id]
         if t.kind == "matrix":
             return 16 * t.count
+        raise NotImplementedError(t.kind)
+
+    def default_value(self, tid):
+        t = self.types[tid]
+        if t.kind == "float":
+            return f32(0)
+        if t.kind == "int":
+            return 0
+        if t.kind == "bool":
+            return False
+        if t.kind == "vector":
+            return [self.default_value(t.elem) for _ in range(t.count)]
+        if t.kind == "matrix":
+            return [self.default_value(t.col) for _ in range(t.count)]
+        if t.kind == "struct":
+            return [self.default_value(x) for x in t.members]
+        if t.kind == "array":
+            return [self.default_value(t.elem) for _ in range(self.consts[t.length_id])]
+        if t.kind == "pointer":
+            return None
         raise NotImplementedError(t.kind)
 
     def variable_names(self):
@@ -255,13 +312,17 @@ class Machine:
             es = m.type_size(t.elem)
             return [self._load_mem(buf, off + k * es, t.elem) for k in range(t.count)]
         if t.kind == "matrix":
-            ms = mstride or 16
+            rowmajor = isinstance(mstride, tuple)
+            ms = (mstride[0] if rowmajor else mstride) or 16
+            if rowmajor:   # element (row r, column c) lives at r * stride + c * 4: gather each column
+                rows = m.types[t.col].count
+                return [[self._load_mem(buf, off + r * ms + c * 4, m.types[t.col].elem) for r in range(rows)] for c in range(t.count)]
             return [self._load_mem(buf, off + c * ms, t.col) for c in range(t.count)]
         if t.kind == "struct":
             out = []
             for k, mt in enumerate(t.members):
                 d = m.member_decor.get((tid, k), {})
-                out.append(self._load_mem(buf, off + d.get(DEC_OFFSET, 0), mt, d.get(DEC_MATRIX_STRIDE)))
+                out.append(self._load_mem(buf, off + d.get(DEC_OFFSET, 0), mt, _mstride(d)))
             return out
         if t.kind == "array":
             st = m.decor[tid][DEC_ARRAY_STRIDE]
@@ -290,24 +351,7 @@ class Machine:
             raise NotImplementedError("store of " + t.kind)
 
     def _default(self, tid):
-        t = self.m.types[tid]
-        if t.kind == "float":
-            return f32(0)
-        if t.kind == "int":
-            return 0
-        if t.kind == "bool":
-            return False
-        if t.kind == "vector":
-            return [self._default(t.elem) for _ in range(t.count)]
-        if t.kind == "matrix":
-            return [self._default(t.col) for _ in range(t.count)]
-        if t.kind == "struct":
-            return [self._default(x) for x in t.members]
-        if t.kind == "array":
-            return [self._default(t.elem) for _ in range(self.m.consts[t.length_id])]
-        if t.kind == "pointer":
-            return None
-        raise NotImplementedError(t.kind)
+        return self.m.default_value(tid)
 
     # ---- execution -----------------------------------------------------------------------------------------------------
     def dispatch(self, groups):
@@ -498,6 +542,49 @@ class Machine:
                 lod = val(a[5])
                 d = smp.fn(coord[0], coord[1], lod)
                 vals[a[1]] = [f32(d), f32(0), f32(0), f32(1)]
+            elif n == "Undef":
+                vals[a[1]] = self._default(a[0])
+            elif n == "Switch":
+                sel = int(val(a[0]))
+                target = a[1]
+                for k in range(2, len(a), 2):
+                    if a[k] == sel:
+                        target = a[k + 1]
+                pc = labels[target]
+            elif n == "VectorTimesMatrix":      # r_c = dot(v, column c); same left-to-right accumulation as MatrixTimesVector
+                v, mat = val(a[2]), val(a[3])
+                out = []
+                for c in range(len(mat)):
+                    acc = f32(mat[c][0] * v[0])
+                    for r in range(1, len(v)):
+                        acc = f32(acc + f32(mat[c][r] * v[r]))
+                    out.append(acc)
+                vals[a[1]] = out
+            elif n == "ConvertFToU":
+                vals[a[1]] = _map1(_ftou, val(a[2]))
+            elif n == "ShiftRightLogical":
+                vals[a[1]] = _map2(lambda x, y: (int(x) & self._mask(a[0])) >> (int(y) & 31), val(a[2]), val(a[3]))
+            elif n == "ShiftLeftLogical":
+                vals[a[1]] = _map2(lambda x, y: (int(x) << (int(y) & 31)) & self._mask(a[0]), val(a[2]), val(a[3]))
+            elif n == "BitwiseAnd":
+                vals[a[1]] = _map2(lambda x, y: int(x) & int(y), val(a[2]), val(a[3]))
+            elif n == "BitwiseOr":
+                vals[a[1]] = _map2(lambda x, y: int(x) | int(y), val(a[2]), val(a[3]))
+            elif n == "ImageFetch":
+                img, coord = val(a[2]), val(a[3])
+                lod = 0
+                if len(a) > 4:
+                    assert a[4] == 0x2, "only the Lod image operand is supported"
+                    lod = _s32(val(a[5]))
+                d = img.fetch(_s32(coord[0]), _s32(coord[1]), lod)
+                vals[a[1]] = [f32(d), f32(0), f32(0), f32(1)]
+            elif n == "ImageTexelPointer":
+                img = self._load(val(a[2]))
+                vals[a[1]] = MemPtr(img.bytes, 4 * int(val(a[3])), T[a[0]].pointee)
+            elif n == "ImageWrite" and isinstance(val(a[0]), TexelBufferU32):
+                img, coord, texel = val(a[0]), int(val(a[1])), val(a[2])
+                if 0 <= 4 * coord < len(img.bytes):
+                    np.frombuffer(img.bytes, dtype="<u4", count=1, offset=4 * coord)[0] = int(texel[0] if isinstance(texel, list) else texel) & 0xFFFFFFFF
             elif n == "ImageWrite":
                 img, coord, texel = val(a[0]), val(a[1]), val(a[2])
                 arr = img.array
@@ -542,7 +629,7 @@ class Machine:
             if t.kind == "struct":
                 d = m.member_decor.get((tid, i), {})
                 off += d.get(DEC_OFFSET, 0)
-                mstride = d.get(DEC_MATRIX_STRIDE)
+                mstride = _mstride(d)
                 tid = t.members[i]
             elif t.kind in ("array", "rtarray"):
                 off += m.decor[tid][DEC_ARRAY_STRIDE] * i
@@ -551,6 +638,8 @@ class Machine:
                 off += m.type_size(t.elem) * i
                 tid = t.elem
             elif t.kind == "matrix":
+                if isinstance(mstride, tuple):
+                    raise NotImplementedError("access chain into a RowMajor matrix")
                 off += (mstride or 16) * i
                 tid = t.col
             elif t.kind == "pointer":
@@ -592,6 +681,10 @@ class Machine:
             return _map2(lambda p, q: q if p < q else p, x[0], x[1])
         if fn == GLSL_FMIN:
             return _map2(lambda p, q: q if q < p else p, x[0], x[1])
+        if fn == GLSL_UMAX:
+            return _map2(lambda p, q: max(int(p), int(q)), x[0], x[1])
+        if fn == GLSL_UMIN:
+            return _map2(lambda p, q: min(int(p), int(q)), x[0], x[1])
         if fn == GLSL_LENGTH:
             v = x[0]
             acc = f32(v[0] * v[0])
@@ -615,6 +708,21 @@ class Machine:
             mant, e = math.frexp(v)              # v = mant * 2^e, mant in [0.5, 1)
             return f32((e - 1) + (0.5 if mant > 0.5 else 0.0))
         return f32(math.log2(v))                 # correctly rounded binary32 of the (double) log2
+
+
+def _mstride(d):
+    ms = d.get(DEC_MATRIX_STRIDE)
+    return (ms, True) if (ms is not None and d.get(DEC_ROW_MAJOR)) else ms
+
+
+def _ftou(v):
+    """D3D `ftou`: truncate, NaN and negatives -> 0, saturate at 2^32 - 1."""
+    v = float(v)
+    if not (v > 0.0):
+        return 0
+    if v >= 4294967296.0:
+        return 0xFFFFFFFF
+    return int(v)
 
 
 def _s32(x):

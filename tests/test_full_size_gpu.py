@@ -154,3 +154,13 @@ def test_instancing_and_cluster_path_full_size_against_oracle(workload):
             draws, dtot = ctx.read_draws(capi.REC_VK24)
             assert dtot == tot and sha(recs_u32(draws)) == sha(exp), mode
             del draws, exp
+        # bounding sphere + Hi-Z (BASELINE config 4's full test), both Hi-Z variants, against the bench's 1920x1080 depth image
+        ctx.set_depth(w["depth"])
+        for hiz in (capi.HIZ_VK, capi.HIZ_DX):
+            ctx.build_pyramid(hiz)
+            pyr = O.build_pyramid(w["depth"], hiz, threads=threads)
+            exp, tot = O.cluster_cull(*S, w["clusters"], view, d_exp, 1, hiz=hiz, pyramid=pyr, **kw)
+            ctx.cluster_cull(capi.CLUSTER_SPHERE_HIZ, capi.REC_VK24, hiz)
+            draws, dtot = ctx.read_draws(capi.REC_VK24)
+            assert dtot == tot and 0 < tot < d_tot and sha(recs_u32(draws)) == sha(exp), ("sphere_hiz", hiz)
+            del draws, exp

@@ -370,3 +370,134 @@ def test_early_pass_density_switch(capi, medium_scene):
                 ctx.early()
                 got, tot = ctx.read_draws()
                 assert tot == len(exp) and np.array_equal(recs_u32(got), exp)
+
+
+def test_against_reference_hlsl_shader_outputs(capi, built, tables):
+    """CUDA path vs tests/golden/hlsl_golden.npz: outputs of the reference's OWN D3D12 shaders (depthPyramid, drawCull, drawOccFirst,
+    drawOccLate with the point-texel OcclusionCheck, drawOccTemporal, drawInstCountReset + drawInstCull + drawInstCmd) executed by
+    oracle/spirv_interp (oracle/spirv_interp/make_hlsl_golden.py).  Ascending id on both sides: exact equality."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "hlsl_golden.npz"))
+    views = {str(n): g["views"][i:i + 1] for i, n in enumerate(g["view_names"])}
+    objs, transforms = g["objs"], g["transforms"]
+    nl = len(tables["lods"])
+    bucket = int(g["inst_bucket"][0])
+    li = g["inst_lod_instances"]
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(objs, transforms, tables["surfaces"], tables["lods"], lod_instances=li, bucket_capacity=np.full(nl, bucket, dtype=np.uint32))
+        for key, dkey in (("pyramid_odd", "depth_odd"), ("pyramid", "depth")):      # depthPyramid.cs.hlsl (the second one stays bound)
+            ctx.set_depth(g[dkey])
+            ctx.build_pyramid(capi.HIZ_DX)
+            data, whm, offs = ctx.read_pyramid()
+            assert tuple(whm) == tuple(int(x) for x in g[key + "_whm"])
+            assert np.array_equal(data.view(np.uint32), g[key].view(np.uint32)), key
+        for vn in ("inside", "tilted", "all", "ref_default"):                         # drawCull.cs.hlsl
+            ctx.set_view(views[vn])
+            ctx.frustum_lod(capi.LIST_OPAQUE, capi.REC_DX32)
+            got, tot = ctx.read_draws(capi.REC_DX32)
+            assert tot == len(g[f"drawcull_{vn}"]) and np.array_equal(recs_u32(got), g[f"drawcull_{vn}"]), vn
+        for vn in ("inside", "tilted"):
+            ctx.set_view(views[vn])
+            ctx.write_visibility(g["vis0"])
+            ctx.early(capi.REC_DX32)                                                    # drawOccFirst.cs.hlsl
+            got, _ = ctx.read_draws(capi.REC_DX32)
+            assert np.array_equal(recs_u32(got), g[f"occfirst_{vn}"]), vn
+            ctx.temporal(capi.LIST_OPAQUE, capi.REC_DX32, capi.HIZ_DX)                  # drawOccTemporal.hlsl
+            got, _ = ctx.read_draws(capi.REC_DX32)
+            assert np.array_equal(recs_u32(got), g[f"occtemporal_{vn}"]), vn
+            assert np.array_equal(ctx.read_visibility(), g["vis0"]), "the temporal pass must not touch the visibility buffer"
+            ctx.late(capi.REC_DX32, capi.HIZ_DX)                                        # drawOccLate.cs.hlsl
+            got, _ = ctx.read_draws(capi.REC_DX32)
+            assert np.array_equal(recs_u32(got), g[f"occlate_{vn}"]), vn
+            assert np.array_equal(ctx.read_visibility(), g[f"occlate_vis_{vn}"]), vn
+        for vn in ("inside", "all"):                                                   # drawInst*.cs.hlsl
+            ctx.set_view(views[vn])
+            ctx.instanced()
+            cmds, tot = ctx.read_draws(capi.REC_DX32)
+            idx, counters = ctx.read_instances(nl * bucket)
+            assert np.array_equal(counters["instanceCount"], g[f"inst_counts_{vn}"]), vn
+            assert np.array_equal(recs_u32(cmds), g[f"inst_cmds_{vn}"]), vn
+            exp = g[f"inst_indices_{vn}"]
+            for l in range(nl):
+                a, c = int(li["instanceOffset"][l]), int(counters["instanceCount"][l])
+                assert np.array_equal(idx[a:a + c], exp[a:a + c]), f"{vn} bucket {l}"
+    from blitzen_b200 import sceneio, scene
+    head = sceneio.read_blob(os.path.join(os.path.dirname(__file__), "golden", "stress_head_4k.blob"))
+    rviews = scene.reference_views()
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(head["objs"], head["transforms"], head["surfaces"], head["lods"])
+        ctx.set_depth(g["depth"])
+        ctx.build_pyramid(capi.HIZ_DX)
+        for vn in ("default", "cfg1_centre", "cfg1_tilted", "cfg1_all"):
+            ctx.set_view(rviews[vn])
+            ctx.write_visibility(g["head_vis0"])
+            ctx.late(capi.REC_DX32, capi.HIZ_DX)
+            got, _ = ctx.read_draws(capi.REC_DX32)
+            assert np.array_equal(recs_u32(got), g[f"head_occlate_{vn}"]), vn
+            assert np.array_equal(ctx.read_visibility(), g[f"head_occlate_vis_{vn}"]), vn
+
+
+@pytest.mark.parametrize("hiz", [0, 1])
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("list_id", [0, 1])
+def test_temporal_pass(capi, small_scene, hiz, fmt, list_id):
+    """blz_cull_temporal (HlslShaders/CS/drawOccTemporal.hlsl:13-65): frustum + Hi-Z in one pass, no visibility buffer read or written;
+    both Hi-Z variants, both record formats, the opaque and the transparent list."""
+    from blitzen_b200 import scene
+    sc = small_scene
+    W, H = 640, 360
+    view = view_at(position=(380, 380, 380), z_far=2000.0, width=W, height=H)
+    depth = scene.synthetic_depth(W, H, n_rects=40, z_min=20.0, z_max=400.0, seed=99)
+    rw = 6 if fmt == 0 else 8
+    transp = sc["objs"][10000:31000].copy()
+    lst = sc["objs"] if list_id == 0 else transp
+    pyr = O.build_pyramid(depth, hiz)
+    exp, tot, _ = O.cull(lst, sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_TEMPORAL, rec_words=rw, hiz=hiz, pyramid=pyr)
+    fr, ftot, _ = O.cull(lst, sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM, rec_words=rw)
+    vis0 = (np.arange(len(sc["objs"])) % 3 == 0).astype(np.uint32)
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], transparent=transp)
+        ctx.set_view(view)
+        ctx.write_visibility(vis0)
+        ctx.set_depth(depth)
+        ctx.build_pyramid(hiz)
+        for _ in range(2):
+            ctx.temporal(list_id, fmt, hiz)
+            got, gtot = ctx.read_draws(fmt)
+            assert gtot == tot and np.array_equal(recs_u32(got), exp)
+        assert np.array_equal(ctx.read_visibility(), vis0)
+    assert 0 < tot < ftot          # the Hi-Z part rejected something
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_pyramid_4k_and_late(capi, medium_scene, variant):
+    """BASELINE config 5's depth size: 3840x2160 -> 2048x2048 x 11 (Vulkan; the 64x64 tail path of pyramid.cu) / 1920x1080 x 11 (D3D12),
+    then a late pass against it, both bit-exact."""
+    from blitzen_b200 import scene
+    sc = medium_scene
+    W, H = 3840, 2160
+    depth = scene.synthetic_depth(W, H, n_rects=64, z_min=50.0, z_max=1500.0, seed=4)
+    rng = np.random.default_rng(8)
+    depth += (rng.random((H, W), dtype=np.float32) * np.float32(1e-4))
+    exp = O.build_pyramid(depth, variant, threads=8)
+    view = view_at(position=(950, 950, 950), z_far=5000.0, width=W, height=H)
+    n = len(sc["objs"])
+    vis0 = (rng.random(n) < 0.4).astype(np.uint32)
+    l_exp, l_tot, vis_exp = O.cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_LATE, hiz=variant, pyramid=exp, vis=vis0, threads=8)
+    for tma in (1, 0):
+        with make_ctx(capi, sc) as ctx:
+            ctx.set_option("pyramid_tma", tma)
+            ctx.set_depth(depth)
+            ctx.build_pyramid(variant)
+            ctx.build_pyramid(variant)
+            data, (pw, ph, mips), offs = ctx.read_pyramid()
+            assert (pw, ph, mips) == (exp.width, exp.height, exp.mips)
+            assert mips == 11
+            assert np.array_equal(data.view(np.uint32), exp.data[:len(data)].view(np.uint32)), f"4K pyramid mismatch tma={tma}"
+            ctx.set_view(view)
+            ctx.write_visibility(vis0)
+            ctx.late(capi.REC_VK24, variant)
+            got, gtot = ctx.read_draws()
+            assert gtot == l_tot and np.array_equal(recs_u32(got), l_exp)
+            assert np.array_equal(ctx.read_visibility(), vis_exp)
+    assert 0 < int(vis_exp.sum()) < n
