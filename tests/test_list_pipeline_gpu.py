@@ -154,3 +154,23 @@ def test_cluster_cull_tight_capacity_all_modes(capi, small_scene):
             ctx.cluster_cull(mode, capi.REC_VK24, 0)
             draws, dtot = ctx.read_draws(capi.REC_VK24)
             assert dtot == tot and np.array_equal(recs_u32(draws), exp), mode
+
+
+@pytest.mark.parametrize("n", [2048, 3000, 4095, 6144, 8191])
+def test_cluster_expand_odd_tile_counts(capi, tables, n):
+    """Regression: with floor(n / 2048) odd the work-item array of the expand step sat at an odd word offset and its 8-byte
+    accesses faulted ('misaligned address'); every size the other tests use has an even quotient."""
+    from blitzen_b200 import scene
+    view = view_at(position=(0, 0, -80), z_far=1e6)
+    objs, xf = scene.generate(groups=((0, 5.0, n - n // 3), (2, 1.0, n // 3)), multiplier=40.0, prologue=False, prng="counter", seed=n)
+    transforms, _ = scene.assemble_transforms(objs, xf, 0)
+    capacity = 4_000_000
+    d_exp, d_tot = O.cluster_expand(objs, transforms, tables["surfaces"], tables["lods"], view, capacity)
+    assert d_tot > 0
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(objs, transforms, tables["surfaces"], tables["lods"], clusters=tables["clusters"], cluster_dispatch_capacity=capacity, draw_capacity=16)
+        ctx.set_view(view)
+        for _ in range(2):
+            ctx.cluster_expand()
+            got, gtot = ctx.read_cluster_dispatch()
+            assert gtot == d_tot and np.array_equal(got.view(np.uint32).reshape(-1, 3), d_exp)
