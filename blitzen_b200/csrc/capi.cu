@@ -176,7 +176,7 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     CU_TRY(cudaSetDevice(c->device));
     DrawCullParams p{};
     p.objs = c->objs[list]; p.n = c->nObjs[list];
-    p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
+    p.xf = c->xf; p.surfaces = c->surf; p.lods = c->lods;
     p.visibility = c->vis; p.draws = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
     p.numTiles = tiles_for(p.n);                      // re-derived from `items` by the launcher
     rc = ensure_status(c, p.n / kCullMinTile + 2u); if (rc) return rc;
@@ -189,35 +189,28 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.capacity = c->drawCap;
     p.view = make_view_consts(c->view);
     p.pyr = c->pyr;
-    // Early pass, option early_mode: 3 = pipelined visibility-stream kernel (default), 2 = the late pass's visible-id list when valid
-    // (pipelined draw kernel only), 1 = one-shot sparse kernel, 0 = the generic draw kernel.
-    p.visList = c->visList; p.visCount = c->counts + 4;
-    const bool stream = c->optDrawKernel == 1;
-    bool earlyStream = pass == PASS_EARLY && c->optEarlyMode == 3 && p.lodCount < (1u << 20);
-    // The pipelined early pass is built for a sparse visible set (0.06 ms at 3.7 % visible, but 0.45 ms when everything was visible); the
-    // streaming kernel takes 0.18 ms whatever the density.  The early pass itself reports how many previously-visible objects it walked
-    // (device counter -> pinned host word, asynchronous): the value seen here lags by a frame or two and only steers the choice of kernel.
-    const bool earlyAuto = earlyStream && stream && c->optEarlyAuto && c->visTotalHost != nullptr;
+    // Early pass: the pipelined visibility-stream kernel (cull_early.cu) is built for a sparse visible set (0.06 ms at 3.7 % visible, but 0.45 ms
+    // when everything was visible); the streaming kernel (cull_stream.cu, PASS_EARLY) takes 0.18 ms whatever the density.  The early pass itself
+    // reports how many previously-visible objects it walked (device counter -> pinned host word, asynchronous): the value seen here lags by a
+    // frame or two and only steers the choice of kernel.  Option early_mode = 0 forces the streaming kernel.
+    bool earlyStream = pass == PASS_EARLY && c->optEarlyMode != 0 && p.lodCount < (1u << 20);
+    const bool earlyAuto = earlyStream && c->optEarlyAuto && c->visTotalHost != nullptr;
     if (earlyAuto) {
         const uint32_t seen = *static_cast<volatile uint32_t*>(c->visTotalHost);
         if (!c->earlyDense && uint64_t(seen) * 5u > p.n) c->earlyDense = true;
         else if (c->earlyDense && uint64_t(seen) * 7u < p.n) c->earlyDense = false;
         if (c->earlyDense) earlyStream = false;
     }
-    const bool denseNow = earlyAuto && c->earlyDense;      // the streaming kernel (PASS_EARLY) runs this frame
     p.visTotal = (earlyAuto && earlyStream) ? c->counts + 5 : nullptr;   // stays 0 between launches (the kernel re-arms it)
     p.visTotalOut = c->visTotalHost;
-    const bool usesBits = (pass == PASS_LATE && stream) || (earlyStream && c->optEarlyBits);
-    const bool usesWords = (pass == PASS_EARLY || pass == PASS_LATE) && !usesBits;
+    const bool usesBits = pass == PASS_LATE || (earlyStream && c->optEarlyBits);
+    const bool usesWords = pass == PASS_EARLY && !usesBits;
     p.visBits = nullptr;
     if (usesBits) { TRY_RC(ensure_vis_bits(c)); p.visBits = c->visBits; }
     if (usesWords) TRY_RC(ensure_vis_words(c));
-    if (pass == PASS_LATE && stream && !c->optVisWords) p.visibility = nullptr;    // the mask is the state; the u32 form is materialised on demand
+    if (pass == PASS_LATE && !c->optVisWords) p.visibility = nullptr;    // the mask is the state; the u32 form is materialised on demand
     if (earlyStream) CU_TRY(launch_early_stream(p, c->numSMs, c->stream));
-    else if (!denseNow && pass == PASS_EARLY && c->optEarlyMode == 2 && c->visListValid) CU_TRY(launch_early_list(p, c->numSMs, c->stream));
-    else if (!denseNow && pass == PASS_EARLY && c->optEarlyMode >= 1 && p.lodCount < (1u << 20)) CU_TRY(launch_early_sparse(p, c->stream));
-    else if (stream) CU_TRY(launch_stream_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, int(c->optStreamCfg), c->numSMs, c->stream));
-    else CU_TRY(launch_draw_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
+    else CU_TRY(launch_stream_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, int(c->optStreamCfg), c->numSMs, c->stream));
     if (earlyAuto && !earlyStream) {       // dense frame: the streaming kernel does not count; a 2 MB popcount + a 4-byte copy next to a 0.18 ms pass
         TRY_RC(ensure_vis_bits(c));
         CU_TRY(cudaMemsetAsync(c->counts + 5, 0, sizeof(uint32_t), c->stream));
@@ -226,9 +219,8 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
         CU_TRY(cudaMemsetAsync(c->counts + 5, 0, sizeof(uint32_t), c->stream));
     }
     if (pass == PASS_LATE) {
-        c->visListValid = !stream;
-        c->visBitsValid = stream;
-        c->visWordsValid = !stream || c->optVisWords != 0;
+        c->visBitsValid = true;
+        c->visWordsValid = c->optVisWords != 0;
     }
     c->launches++;
     c->lastRecWords = p.recWords;
@@ -243,7 +235,7 @@ int run_survivor_list(blz_cull_ctx* c, int list)
     TRY_RC(grow(c, c->survList, c->capSurvList, size_t(n) * sizeof(uint2) + 16u));
     DrawCullParams p{};
     p.objs = c->objs[list]; p.n = n;
-    p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
+    p.xf = c->xf; p.surfaces = c->surf; p.lods = c->lods;
     p.visibility = nullptr; p.draws = reinterpret_cast<uint32_t*>(c->survList); p.counts = c->counts + 6; p.ctl = c->ctl;
     p.numTiles = tiles_for(p.n);
     TRY_RC(ensure_status(c, p.n / kCullMinTile + 2u));
@@ -304,13 +296,13 @@ int blz_cull_create(int device, blz_cull_ctx** out)
 static void free_scene(blz_cull_ctx* c)
 {
     for (int i = 0; i < 3; ++i) { dfree(c->objs[i]); c->nObjs[i] = 0; }
-    dfree(c->xfPS); dfree(c->xfQ); dfree(c->xfStage); c->nXf = 0; c->xfStageCap = 0;
+    dfree(c->xf); c->nXf = 0;
     dfree(c->surf); dfree(c->lods); dfree(c->clusters); dfree(c->lodInst); dfree(c->bucketCap);
-    dfree(c->vis); dfree(c->visList); dfree(c->visBits); dfree(c->draws); dfree(c->drawsAlt); dfree(c->dispatch); dfree(c->instIdx); dfree(c->survList); dfree(c->listScratch); c->capSurvList = 0; c->capListScratch = 0;
-    c->capVisList = 0; c->visListValid = false; c->capVisBits = 0; c->visBitsValid = false;
+    dfree(c->vis); dfree(c->visBits); dfree(c->draws); dfree(c->drawsAlt); dfree(c->dispatch); dfree(c->instIdx); dfree(c->survList); dfree(c->listScratch); c->capSurvList = 0; c->capListScratch = 0;
+    c->capVisBits = 0; c->visBitsValid = false;
     c->nSurf = c->nLods = c->nClusters = c->nLodInst = 0; c->drawCap = c->dispatchCap = c->instCap = 0;
     c->capObjs[0] = c->capObjs[1] = c->capObjs[2] = 0;
-    c->capXfPS = c->capXfQ = c->capSurf = c->capLods = c->capClusters = c->capLodInst = c->capBucket = 0;
+    c->capXf = c->capSurf = c->capLods = c->capClusters = c->capLodInst = c->capBucket = 0;
     c->capVis = c->capDraws = c->capDispatch = c->capInstIdx = 0;
 }
 
@@ -373,22 +365,10 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
         TRY_RC(grow(c, c->objs[i], c->capObjs[i], size_t(counts[i]) * sizeof(RenderObject) + 16u));     // + 16: bulk copies of the ragged last tile are rounded up to 16 B
         CU_TRY(cudaMemcpyAsync(c->objs[i], lists[i], size_t(counts[i]) * sizeof(RenderObject), kind, c->stream));
     }
-    // transforms: AoS staging -> SoA repack (the per-frame path only reads the two SoA streams)
+    // transforms: kept AoS exactly as uploaded (32-byte records; cudaMalloc aligns to 256 B, so every record is one aligned 256-bit load)
     c->nXf = d->transform_count;
-    TRY_RC(grow(c, c->xfPS, c->capXfPS, size_t(c->nXf) * sizeof(float4)));
-    TRY_RC(grow(c, c->xfQ, c->capXfQ, size_t(c->nXf) * sizeof(float4)));
-    {
-        const MeshTransform* src = reinterpret_cast<const MeshTransform*>(d->transforms);
-        if (!d->inputs_on_device) {
-            size_t capB = size_t(c->xfStageCap) * sizeof(MeshTransform);
-            TRY_RC(grow(c, c->xfStage, capB, size_t(c->nXf) * sizeof(MeshTransform)));
-            c->xfStageCap = uint32_t(capB / sizeof(MeshTransform));
-            CU_TRY(cudaMemcpyAsync(c->xfStage, d->transforms, size_t(c->nXf) * sizeof(MeshTransform), cudaMemcpyHostToDevice, c->stream));
-            src = c->xfStage;
-        }
-        CU_TRY(launch_repack_transforms(src, c->xfPS, c->xfQ, 0, c->nXf, c->stream));
-        c->launches++;
-    }
+    TRY_RC(grow(c, c->xf, c->capXf, size_t(c->nXf) * sizeof(MeshTransform)));
+    CU_TRY(cudaMemcpyAsync(c->xf, d->transforms, size_t(c->nXf) * sizeof(MeshTransform), kind, c->stream));
     c->nSurf = d->surface_count; c->nLods = d->lod_count;
     TRY_RC(grow(c, c->surf, c->capSurf, size_t(c->nSurf) * sizeof(PrimitiveSurface)));
     CU_TRY(cudaMemcpyAsync(c->surf, d->surfaces, size_t(c->nSurf) * sizeof(PrimitiveSurface), kind, c->stream));
@@ -405,8 +385,6 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     const size_t nVis = c->nObjs[0] ? c->nObjs[0] : 1;
     TRY_RC(grow(c, c->vis, c->capVis, nVis * sizeof(uint32_t) + 16u));
     CU_TRY(cudaMemsetAsync(c->vis, 0, nVis * sizeof(uint32_t), c->stream));
-    TRY_RC(grow(c, c->visList, c->capVisList, nVis * sizeof(uint32_t)));
-    c->visListValid = false;
     const size_t bitBytes = ((nVis + 4095) / 4096) * 512 + 512;                        // whole 4096-object tiles of the bit-mask early pass
     TRY_RC(grow(c, c->visBits, c->capVisBits, bitBytes));
     CU_TRY(cudaMemsetAsync(c->visBits, 0, c->capVisBits, c->stream));
@@ -462,15 +440,8 @@ int blz_cull_update_transforms(blz_cull_ctx* c, uint32_t first, uint32_t count, 
     if (first < c->transformIdBase || uint64_t(first - c->transformIdBase) + count > c->nXf)
         return fail(BLZ_ERR_INVALID, "transform range [%u, %u) outside this context's [%u, %u)", first, first + count, c->transformIdBase, c->transformIdBase + c->nXf);
     CU_TRY(cudaSetDevice(c->device));
-    if (count > c->xfStageCap) {
-        CU_TRY(cudaStreamSynchronize(c->stream));
-        dfree(c->xfStage);
-        CU_TRY(cudaMalloc(&c->xfStage, size_t(count) * sizeof(MeshTransform)));
-        c->xfStageCap = count;
-    }
-    CU_TRY(cudaMemcpyAsync(c->xfStage, host, size_t(count) * sizeof(MeshTransform), cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(launch_repack_transforms(c->xfStage, c->xfPS, c->xfQ, first - c->transformIdBase, count, c->stream));
-    c->launches++;
+    // UpdateObjectTransform / UpdateBuffers (BlitzenVulkan/vulkanDraw.cpp:46-60, :816-820): a stream-ordered copy straight into place
+    CU_TRY(cudaMemcpyAsync(c->xf + (first - c->transformIdBase), host, size_t(count) * sizeof(MeshTransform), cudaMemcpyHostToDevice, c->stream));
     return BLZ_OK;
 }
 
@@ -489,7 +460,7 @@ int blz_cull_reset_visibility(blz_cull_ctx* c)
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMemsetAsync(c->vis, 0, size_t(c->nObjs[0] ? c->nObjs[0] : 1) * sizeof(uint32_t), c->stream));
     CU_TRY(cudaMemsetAsync(c->visBits, 0, c->capVisBits, c->stream));
-    c->visListValid = false; c->visBitsValid = true; c->visWordsValid = true;
+    c->visBitsValid = true; c->visWordsValid = true;
     return BLZ_OK;
 }
 
@@ -499,7 +470,7 @@ int blz_cull_write_visibility(blz_cull_ctx* c, const uint32_t* host)
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMemcpyAsync(c->vis, host, size_t(c->nObjs[0]) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
-    c->visListValid = false; c->visBitsValid = false; c->visWordsValid = true;
+    c->visBitsValid = false; c->visWordsValid = true;
     return BLZ_OK;
 }
 
@@ -581,32 +552,18 @@ int blz_cull_instanced(blz_cull_ctx* c, int list)
     if (!c->lodInst) return fail(BLZ_ERR_INVALID, "scene was uploaded without lod_instances");
     if (c->nLods > 256) return fail(BLZ_ERR_CAPACITY, "instancing supports at most 256 LODs (scene has %u)", c->nLods);
     CU_TRY(cudaSetDevice(c->device));
-    if (c->optListPipeline && c->nLods < (1u << 18)) {
-        TRY_RC(run_survivor_list(c, list));
-        TRY_RC(grow(c, c->listScratch, c->capListScratch, size_t(c->nLods) * kListMaxTiles * sizeof(uint32_t)));
-        ListInstanceParams q{};
-        q.list = c->survList; q.listCount = c->counts + 6; q.maxEntries = c->nObjs[list];
-        q.lodInstances = c->lodInst; q.bucketCapacity = c->bucketCap; q.instanceIndices = c->instIdx;
-        q.lods = c->lods; q.lodCount = c->nLods;
-        q.cmds = c->draws; q.counts = c->drawCounts; q.cmdCapacity = c->drawCap;
-        q.hist = c->listScratch;
-        CU_TRY(launch_list_instancing(q, c->stream));
-        c->launches += 2;
-        c->lastRecWords = 8u;
-        return BLZ_OK;
-    }
-    InstanceCullParams p{};
-    p.objs = c->objs[list]; p.n = c->nObjs[list]; p.numTiles = tiles_for(p.n);
-    p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
-    p.lodInstances = c->lodInst; p.bucketCapacity = c->bucketCap; p.instanceIndices = c->instIdx;
-    p.cmds = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
-    rc = ensure_status(c, size_t(p.numTiles) * c->nLods); if (rc) return rc;
-    p.status = c->status;
-    p.objectIdBase = list == BLZ_LIST_OPAQUE ? c->objectIdBase : 0u; p.transformIdBase = c->transformIdBase;
-    p.surfaceCount = c->nSurf; p.lodCount = c->nLods; p.cmdCapacity = c->drawCap;
-    p.view = make_view_consts(c->view);
-    CU_TRY(launch_instance_cull(p, c->numSMs, c->stream));
-    c->launches++;
+    if (c->nLods >= (1u << 18)) return fail(BLZ_ERR_CAPACITY, "survivor-list descriptors hold 18 bits of LOD id (scene has %u LODs)", c->nLods);
+    // step 1: streaming frustum + LOD pass -> survivor list {objectId, absolute LOD id}; step 2: stable counting sort by LOD (cull_list.cu)
+    TRY_RC(run_survivor_list(c, list));
+    TRY_RC(grow(c, c->listScratch, c->capListScratch, size_t(c->nLods) * kListMaxTiles * sizeof(uint32_t)));
+    ListInstanceParams q{};
+    q.list = c->survList; q.listCount = c->counts + 6; q.maxEntries = c->nObjs[list];
+    q.lodInstances = c->lodInst; q.bucketCapacity = c->bucketCap; q.instanceIndices = c->instIdx;
+    q.lods = c->lods; q.lodCount = c->nLods;
+    q.cmds = c->draws; q.counts = c->drawCounts; q.cmdCapacity = c->drawCap;
+    q.hist = c->listScratch;
+    CU_TRY(launch_list_instancing(q, c->stream));
+    c->launches += 2;
     c->lastRecWords = 8u;
     return BLZ_OK;
 }
@@ -617,29 +574,16 @@ int blz_cull_cluster_expand(blz_cull_ctx* c, int list)
     int rc = check_list(c, list); if (rc) return rc;
     if (!c->dispatch) return fail(BLZ_ERR_INVALID, "scene was uploaded with cluster_dispatch_capacity = 0");
     CU_TRY(cudaSetDevice(c->device));
-    if (c->optListPipeline && c->nLods < (1u << 18)) {
-        TRY_RC(run_survivor_list(c, list));
-        TRY_RC(grow(c, c->listScratch, c->capListScratch, list_expand_scratch_words(c->nObjs[list], c->dispatchCap) * sizeof(uint32_t)));
-        ListExpandParams q{};
-        q.list = c->survList; q.listCount = c->counts + 6; q.maxEntries = c->nObjs[list];
-        q.lods = c->lods; q.lodCount = c->nLods;
-        q.dispatch = c->dispatch; q.counts = c->counts + 2; q.capacity = c->dispatchCap;
-        list_expand_carve(c->listScratch, c->nObjs[list], q); q.ctl = c->ctl;
-        CU_TRY(launch_list_expand(q, c->numSMs, c->stream));
-        c->launches += 2;
-        return BLZ_OK;
-    }
-    ClusterExpandParams p{};
-    p.objs = c->objs[list]; p.n = c->nObjs[list]; p.numTiles = tiles_for(p.n);
-    p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.surfaces = c->surf; p.lods = c->lods;
-    p.dispatch = c->dispatch; p.counts = c->counts + 2; p.ctl = c->ctl;
-    rc = ensure_status(c, p.numTiles); if (rc) return rc;
-    p.status = c->status;
-    p.objectIdBase = list == BLZ_LIST_OPAQUE ? c->objectIdBase : 0u; p.transformIdBase = c->transformIdBase;
-    p.surfaceCount = c->nSurf; p.lodCount = c->nLods; p.capacity = c->dispatchCap;
-    p.view = make_view_consts(c->view);
-    CU_TRY(launch_cluster_expand(p, c->numSMs, c->stream));
-    c->launches++;
+    if (c->nLods >= (1u << 18)) return fail(BLZ_ERR_CAPACITY, "survivor-list descriptors hold 18 bits of LOD id (scene has %u LODs)", c->nLods);
+    TRY_RC(run_survivor_list(c, list));
+    TRY_RC(grow(c, c->listScratch, c->capListScratch, list_expand_scratch_words(c->nObjs[list], c->dispatchCap) * sizeof(uint32_t)));
+    ListExpandParams q{};
+    q.list = c->survList; q.listCount = c->counts + 6; q.maxEntries = c->nObjs[list];
+    q.lods = c->lods; q.lodCount = c->nLods;
+    q.dispatch = c->dispatch; q.counts = c->counts + 2; q.capacity = c->dispatchCap;
+    list_expand_carve(c->listScratch, c->nObjs[list], q); q.ctl = c->ctl;
+    CU_TRY(launch_list_expand(q, c->numSMs, c->stream));
+    c->launches += 2;
     return BLZ_OK;
 }
 
@@ -655,7 +599,7 @@ int blz_cull_cluster_cull(blz_cull_ctx* c, int mode, int fmt, int hiz)
     CU_TRY(cudaSetDevice(c->device));
     ClusterCullParams p{};
     p.dispatch = c->dispatch; p.dispatchCount = c->counts + 2;
-    p.objs = c->objs[BLZ_LIST_OPAQUE]; p.xfPosScale = c->xfPS; p.xfQuat = c->xfQ; p.clusters = c->clusters;
+    p.objs = c->objs[BLZ_LIST_OPAQUE]; p.xf = c->xf; p.clusters = c->clusters;
     p.draws = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
     p.maxRecords = uint32_t(c->dispatchCap > 0xFFFFFFFFull ? 0xFFFFFFFFull : c->dispatchCap);
     int rc = ensure_status(c, size_t(p.maxRecords) / kCullMinTile + 2u); if (rc) return rc;   // the kernel's tile is 512..1024 records (launch_cluster_cull)
@@ -791,14 +735,12 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (strcmp(name, "early_mode") == 0) { c->optEarlyMode = value; return BLZ_OK; }
     if (strcmp(name, "early_bits") == 0) { c->optEarlyBits = value; return BLZ_OK; }
     if (strcmp(name, "vis_words") == 0) { c->optVisWords = value; return BLZ_OK; }
-    if (strcmp(name, "draw_kernel") == 0) { c->optDrawKernel = value; return BLZ_OK; }
     if (strcmp(name, "l2_fetch_granularity") == 0) {           // 32 / 64 / 128 bytes: device-wide hint (cudaLimitMaxL2FetchGranularity); the sparse early pass gathers 8-16 B per 200-400 B
         CU_TRY(cudaSetDevice(c->device));
         CU_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(value)));
         return BLZ_OK;
     }
     if (strcmp(name, "early_auto") == 0) { c->optEarlyAuto = value; c->earlyDense = false; return BLZ_OK; }
-    if (strcmp(name, "list_pipeline") == 0) { c->optListPipeline = value; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     if (strcmp(name, "stream_dynamic") == 0) { c->optStreamDynamic = value; return BLZ_OK; }
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);

@@ -10,8 +10,7 @@ struct blz_cull_ctx {
     // scene (device)
     blz::RenderObject* objs[3] = { nullptr, nullptr, nullptr };
     uint32_t nObjs[3] = { 0, 0, 0 };
-    float4 *xfPS = nullptr, *xfQ = nullptr; uint32_t nXf = 0;
-    blz::MeshTransform* xfStage = nullptr; uint32_t xfStageCap = 0;
+    blz::MeshTransform* xf = nullptr; uint32_t nXf = 0;       // AoS as uploaded: the kernels read one 32-byte record with one 256-bit load
     blz::PrimitiveSurface* surf = nullptr; uint32_t nSurf = 0;
     blz::LodData* lods = nullptr; uint32_t nLods = 0;
     blz::Cluster* clusters = nullptr; uint32_t nClusters = 0;
@@ -19,18 +18,16 @@ struct blz_cull_ctx {
     uint32_t* bucketCap = nullptr;
     uint32_t objectIdBase = 0, transformIdBase = 0;
     // allocation sizes in bytes (buffers only ever grow; see grow() in capi.cu)
-    size_t capObjs[3] = { 0, 0, 0 }, capXfPS = 0, capXfQ = 0, capSurf = 0, capLods = 0, capClusters = 0, capLodInst = 0, capBucket = 0;
+    size_t capObjs[3] = { 0, 0, 0 }, capXf = 0, capSurf = 0, capLods = 0, capClusters = 0, capLodInst = 0, capBucket = 0;
     size_t capVis = 0, capDraws = 0, capDispatch = 0, capInstIdx = 0;
     // per-object state + outputs
     uint32_t* vis = nullptr;
     uint32_t* draws = nullptr; uint64_t drawCap = 0;
-    uint32_t* counts = nullptr;               // [0..1] draws (slot 0), [2..3] cluster dispatch, [4] length of visList, [6..7] survivor list, [8..9] draws (slot 1)
+    uint32_t* counts = nullptr;               // [0..1] draws (slot 0), [2..3] cluster dispatch, [5] early-pass density accumulator, [6..7] survivor list, [8..9] draws (slot 1)
     uint32_t* drawCounts = nullptr;           // counts + 0 or counts + 8: {written, total} of the current draw buffer
-    uint32_t* visList = nullptr; size_t capVisList = 0;   // ascending ids the last late pass found visible
     uint32_t* visBits = nullptr; size_t capVisBits = 0;   // 1 bit per object, padded to whole early-pass tiles
     bool visBitsValid = false;                // visBits is current
     bool visWordsValid = false;               // vis (u32 per object, the reference's form) is current; at least one of the two always is
-    bool visListValid = false;                // true while visibility[] has not been written by anything but that late pass
     uint32_t* dispatch = nullptr; uint64_t dispatchCap = 0;
     uint32_t* instIdx = nullptr; uint64_t instCap = 0;
     uint32_t* visTotalHost = nullptr;         // pinned: number of previously-visible objects the last COMPLETED early pass saw (lags by a frame; a hint only)
@@ -50,13 +47,11 @@ struct blz_cull_ctx {
     blz::CameraViewData view{}; bool haveView = false;
     uint64_t launches = 0;
     int64_t optPyramidTma = 1;
-    int64_t optEarlyMode = 3;                 // 3 = pipelined visibility-stream kernel, 2 = visible list when valid else sparse, 1 = one-shot sparse kernel, 0 = generic draw kernel
+    int64_t optEarlyMode = 1;                 // 1 = pipelined visibility-stream kernel (cull_early.cu), 0 = the streaming kernel (cull_stream.cu, PASS_EARLY) whatever the density
     int64_t optEarlyBits = 1;                 // pipelined early pass streams the 1-bit mask (1) or the 4-B visibility words (0)
     int64_t optVisWords = 0;                  // 1: the streaming late pass also writes the u32-per-object visibility buffer every frame (else on demand)
-    int64_t optDrawKernel = 1;                // 0 = pipelined kernel (cull_draw.cu), 1 = streaming kernel (cull_stream.cu)
     int64_t optStreamDynamic = 1;             // streaming kernel: atomic-ticket tile order (1) or static round-robin (0)
-    int64_t optEarlyAuto = 1;                 // early_mode 3: switch to the streaming kernel while more than ~20 % of the objects were visible last frame
-    int64_t optListPipeline = 1;              // instancing / cluster expand: 1 = streaming frustum pass -> survivor list -> cull_list.cu, 0 = one-shot kernels (cull_inst_cluster.cu)
+    int64_t optEarlyAuto = 1;                 // early_mode 1: switch to the streaming kernel while more than ~20 % of the objects were visible last frame
     int64_t optStreamCfg = 2;                 // CTA shape of the streaming kernel (see launch_pass in cull_stream.cu)
     uint32_t lastRecWords = 6;                // record width (u32 words) of the pass that last wrote `draws`
     // gather (multi-GPU): the presenter owns gatherBuf/gatherFlags; every rank (presenter included) writes through gatherDst*

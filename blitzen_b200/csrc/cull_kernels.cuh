@@ -7,25 +7,18 @@ namespace blz {
 constexpr int kCullThreads = 256;                    // 8 warps per CTA
 constexpr int kCullItems = 4;                        // objects per thread
 constexpr int kCullTile = kCullThreads * kCullItems; // objects per tile (one ticket) of the instancing / cluster kernels
-constexpr int kDrawThreads = 512;                    // draw-cull kernels: 16 warps per CTA, 2 CTAs per SM ...
-constexpr int kDrawDenseWarps = 12;                  // ... 12 of them stream objects (sphere + frustum), 4 evaluate the survivor queue (Hi-Z, LOD)
-constexpr int kDrawItems = 2;
-constexpr int kDrawTile = kDrawDenseWarps * 32 * kDrawItems;   // 768 objects per tile
 constexpr int kCullMinTile = 512;                    // smallest tile any kernel uses: sizes the per-tile status array
 
 struct DrawCullParams {
     // inputs
     const RenderObject* objs;        // AoS, 8 B, the reference layout (two u32)
-    const float4* xfPosScale;        // SoA repack of MeshTransform: {pos.xyz, scale}
-    const float4* xfQuat;            // SoA repack of MeshTransform: orientation
+    const MeshTransform* xf;         // AoS, 32 B, the reference layout as uploaded (one 256-bit load per object); 32-byte aligned
     const PrimitiveSurface* surfaces;
     const LodData* lods;
     uint32_t* visibility;            // u32 per object (early: read, late: read + write)
     // outputs
     uint32_t* draws;                 // records, recWords u32 each
     uint32_t* counts;                // [0] = written (clamped to capacity), [1] = total
-    uint32_t* visList;               // late pass: ascending LOCAL indices of the objects it found visible (may be null); early-list pass: its input
-    uint32_t* visCount;              // device word holding the length of visList
     uint32_t* visTotal;              // pipelined early pass: += number of previously-visible objects it walked (may be null) ...
     uint32_t* visTotalOut;           // ... and the last CTA out stores the total here (host-mapped pinned word) and zeroes the accumulator
     uint32_t* visBits;               // 1 bit per object (word i = objects 32i..32i+31): written by the streaming late pass, source of the pipelined early pass (may be null)
@@ -44,35 +37,10 @@ struct DrawCullParams {
     PyramidDesc pyr;
 };
 
-struct InstanceCullParams {
-    const RenderObject* objs; const float4* xfPosScale; const float4* xfQuat;
-    const PrimitiveSurface* surfaces; const LodData* lods;
-    LodInstanceCounter* lodInstances;     // instanceOffset read, instanceCount written (total survivors of the LOD)
-    const uint32_t* bucketCapacity;       // per LOD
-    uint32_t* instanceIndices;
-    uint32_t* cmds;                       // DX32 records
-    uint32_t* counts;                     // [0] = written cmds, [1] = total cmds
-    ScanCtl* ctl; uint64_t* status;       // status[tile * lodCount + lod]
-    uint32_t n, numTiles, objectIdBase, transformIdBase, surfaceCount, lodCount;
-    uint64_t cmdCapacity;
-    ViewConsts view;
-};
-
-struct ClusterExpandParams {
-    const RenderObject* objs; const float4* xfPosScale; const float4* xfQuat;
-    const PrimitiveSurface* surfaces; const LodData* lods;
-    uint32_t* dispatch;                   // ClusterDispatchData records (3 u32)
-    uint32_t* counts;                     // [0] = written, [1] = total
-    ScanCtl* ctl; uint64_t* status;
-    uint32_t n, numTiles, objectIdBase, transformIdBase, surfaceCount, lodCount;
-    uint64_t capacity;
-    ViewConsts view;
-};
-
 struct ClusterCullParams {
     const uint32_t* dispatch;             // ClusterDispatchData records
     const uint32_t* dispatchCount;        // device: [0] = number of records (stays on the device)
-    const RenderObject* objs; const float4* xfPosScale; const float4* xfQuat;
+    const RenderObject* objs; const MeshTransform* xf;
     const Cluster* clusters;
     uint32_t* draws; uint32_t* counts;
     ScanCtl* ctl; uint64_t* status;
@@ -110,18 +78,12 @@ cudaError_t launch_list_instancing(const ListInstanceParams& p, cudaStream_t str
 cudaError_t launch_list_expand(const ListExpandParams& p, int numSMs, cudaStream_t stream);
 
 // launchers (return the cudaError_t of the launch)
-cudaError_t launch_draw_cull(const DrawCullParams& p, int pass, int hiz, int numSMs, cudaStream_t stream);
 cudaError_t launch_stream_cull(const DrawCullParams& p, int pass, int hiz, int cfg, int numSMs, cudaStream_t stream);   // cull_stream.cu
 cudaError_t launch_early_stream(const DrawCullParams& p, int numSMs, cudaStream_t stream);   // cull_early.cu: pipelined early pass (default)
 cudaError_t launch_pack_vis_bits(const uint32_t* vis, uint32_t* bits, uint32_t n, cudaStream_t stream);   // cull_early.cu
 cudaError_t launch_unpack_vis_bits(const uint32_t* bits, uint32_t* vis, uint32_t n, cudaStream_t stream); // cull_early.cu
 cudaError_t launch_popc_vis_bits(const uint32_t* bits, uint32_t n, uint32_t* total, cudaStream_t stream);   // cull_early.cu
-cudaError_t launch_early_sparse(const DrawCullParams& p, cudaStream_t stream);
-cudaError_t launch_early_list(const DrawCullParams& p, int numSMs, cudaStream_t stream);   // cull_early.cu: PASS_EARLY over the late pass's visible list   // cull_early.cu: PASS_EARLY for mostly-invisible scenes
-cudaError_t launch_instance_cull(const InstanceCullParams& p, int numSMs, cudaStream_t stream);
-cudaError_t launch_cluster_expand(const ClusterExpandParams& p, int numSMs, cudaStream_t stream);
 cudaError_t launch_cluster_cull(const ClusterCullParams& p, int hiz, int numSMs, cudaStream_t stream);
-cudaError_t launch_repack_transforms(const MeshTransform* aos, float4* posScale, float4* quat, uint32_t first, uint32_t count, cudaStream_t stream);
 
 struct PyramidBuildParams {
     const float* depth; uint32_t depthW, depthH;

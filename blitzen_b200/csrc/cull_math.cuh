@@ -22,6 +22,14 @@ __device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
 
 struct Sphere { float x, y, z, r; };
 
+// The reference's 32-byte MeshTransform {pos.xyz, scale, orientation} (Resources/renderingResourcesTypes.h:124-129) read as uploaded, with
+// ONE 256-bit load per object (sm_100 LDG.E.256): one request and exactly one 32-byte sector per gathered transform.
+__device__ __forceinline__ void ld_transform(const MeshTransform* p, float4& ps, float4& qt)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(ps.x), "=f"(ps.y), "=f"(ps.z), "=f"(ps.w), "=f"(qt.x), "=f"(qt.y), "=f"(qt.z), "=f"(qt.w) : "l"(p));
+}
+
 // view-space bounding sphere: center = RotateQuat(bc, q) * scale + pos; center = (view * vec4(center, 1)).xyz; radius = br * scale
 __device__ __forceinline__ Sphere view_space_sphere(float bcx, float bcy, float bcz, float br,
                                                     float px, float py, float pz, float scale,

@@ -67,7 +67,7 @@ constexpr uint32_t kSLocalMask = (1u << kSLocalBits) - 1u;
 // Evaluates queue entry e of a warp's private queue: Hi-Z (late / temporal passes) and LOD selection for emitters.
 // Returns visible | emit << 1 | lodId << 2.
 template <int PASS, int HIZ>
-__device__ __forceinline__ uint32_t eval_entry(const float4 q, const uint2 m /* {scale bits, index in tile | visPrev << 16} */, const uint32_t sidx,
+__device__ __forceinline__ uint32_t eval_entry(const float4 q, const uint32_t scaleBits, const bool visPrev, const uint32_t sidx,
                                                const PrimitiveSurface* surfT, const LodData* lodT, const DrawCullParams& p)
 {
     constexpr bool HAS_HIZ = (PASS == PASS_LATE || PASS == PASS_TEMPORAL);
@@ -80,11 +80,11 @@ __device__ __forceinline__ uint32_t eval_entry(const float4 q, const uint2 m /* 
             visible = (HIZ == HIZ_VK) ? hiz_test_vk(aabb, p.pyr, s, V) : hiz_test_dx(aabb, p.pyr, s, V);
     }
     bool emit = visible;
-    if (PASS == PASS_LATE) emit = visible && ((m.y >> 16) == 0u);                  // LateDrawCull.comp.glsl:49
+    if (PASS == PASS_LATE) emit = visible && !visPrev;                             // LateDrawCull.comp.glsl:49
     uint32_t lodId = 0u;
     if (emit) {
         const uint32_t lodOffset = surfT[sidx].lodOffset, lodCount = surfT[sidx].lodCount;
-        const uint32_t rel = lod_select(s, __uint_as_float(m.x), V.lodTarget, lodOffset, lodCount, [&](uint32_t li) { return lodT[li].error; });
+        const uint32_t rel = lod_select(s, __uint_as_float(scaleBits), V.lodTarget, lodOffset, lodCount, [&](uint32_t li) { return lodT[li].error; });
         lodId = (p.flags & kFlagOnpcLodQuirk) ? rel : rel + lodOffset;
     }
     return (visible ? 1u : 0u) | (emit ? 2u : 0u) | (lodId << 2);
@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
     __shared__ uint32_t s_totals[4];         // records of the tile computed in iteration j, at [j & 3]
     __shared__ uint32_t s_sum[4];            // sum of the aggregates between this CTA's consecutive tiles, at [j & 3]
     __shared__ uint32_t s_tiles[8];          // dynamic order: the CTA's m-th tile at [m & 7]
+    __shared__ uint32_t s_visPrev[2][VIS_BITS ? THREADS * ITEMS / 32 : 1];   // late pass: last frame's mask words of the tile fetched in iteration j-1, at [j & 1] (the ring stage is refilled before the queue is evaluated)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t laneLt = (1u << lane) - 1u;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
     unsigned char* sp = smem_raw;
     uint2* objRing = reinterpret_cast<uint2*>(sp);       sp += size_t(D) * TILE * sizeof(uint2);      // TMA destination: RenderObject stream
     uint32_t* visRing = reinterpret_cast<uint32_t*>(sp); sp += size_t(D) * VIS_STAGE_WORDS * sizeof(uint32_t);     // TMA destination: visibility stream (words or mask)
-    // per-warp private survivor queue, WSPAN entries of 32 B: {view-space sphere} {scale bits, index in tile | visPrev << 16, surfaceId, D}
+    // per-warp private survivor queue, WSPAN entries of 32 B: {view-space sphere} {scale bits, index in tile, surfaceId, D}
     // where D of entry i is the i-th EMITTER descriptor of the span (a compact list threaded through the entries' last words: it is
     // written by the evaluation of entry e >= i and nothing else reads that word)
     uint4* queue = reinterpret_cast<uint4*>(sp) + warp * (WSPAN * 2);   sp += size_t(TILE) * 32;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
     // registers carried from the fetch of a tile (iteration j-1) to its arithmetic (iteration j)
     float4 ps[ITEMS], qt[ITEMS];
     uint32_t sid[ITEMS];
-    uint32_t actMask = 0u, inMask = 0u, vpMask = 0u;
+    uint32_t actMask = 0u, inMask = 0u;
     uint32_t curTile = kNoTile, prev1 = kNoTile, prev2 = kNoTile;      // tiles of iterations j, j-1, j-2 (prev2's records go out in iteration j)
     uint32_t cum = 0u;                       // records emitted by tiles [0, nextRead)
     uint32_t nextRead = 0u;                  // first tile whose aggregate this CTA has not summed yet
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
                     if ((survMask >> k) & 1u) {
                         uint4* e = queue + 2u * (qn + uint32_t(__popc(ball & laneLt)));
                         e[0] = make_uint4(__float_as_uint(sph[k].x), __float_as_uint(sph[k].y), __float_as_uint(sph[k].z), __float_as_uint(sph[k].r));
-                        e[1] = make_uint4(__float_as_uint(ps[k].w), (localBase + uint32_t(k) * 32u) | (((vpMask >> k) & 1u) << 16), sid[k], 0u);   // last iteration's descriptors are staged: D is free
+                        e[1] = make_uint4(__float_as_uint(ps[k].w), localBase + uint32_t(k) * 32u, sid[k], 0u);   // last iteration's descriptors are staged: D is free
                     }
                     qn += uint32_t(__popc(ball));
                 }
@@ -294,22 +295,29 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
             const uint2* ob = objRing + stage * TILE + localBase;
             const uint32_t* vr = visRing + stage * VIS_STAGE_WORDS + (VIS_WORDS ? localBase : warp * uint32_t(ITEMS));
             const uint32_t left = p.n - nextTile * uint32_t(TILE);         // objects from the tile's first to the end of the list (>= 1)
-            actMask = 0u; inMask = 0u; vpMask = 0u;
+            if (PASS != PASS_EARLY && left >= uint32_t(TILE)) {
+                // a full tile (all but the last one): every item is in range and active -- per object one 64-bit shared load, one subtract,
+                // one address and one 256-bit gather, no predicates and no mask bookkeeping
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) {
-                const bool in = localBase + uint32_t(k) * 32u < left;
-                const uint2 o = ob[k * 32];
-                const uint32_t v = VIS_WORDS ? vr[k * 32] : (VIS_BITS ? ((vr[k] >> lane) & 1u) : 0u);
-                const bool vprev = in && v != 0u;
-                const bool act = (PASS == PASS_EARLY) ? vprev : in;                        // InitialDrawCull.comp.glsl:21-24
-                sid[k] = in ? o.y : 0u;                                                    // the ragged tail of the ring holds stale words
-                if (act) {
-                    const uint32_t t = o.x - p.transformIdBase;
-                    ps[k] = ld_stream_f4(p.xfPosScale + t);
-                    qt[k] = ld_stream_f4(p.xfQuat + t);
+                for (int k = 0; k < ITEMS; ++k) {
+                    const uint2 o = ob[k * 32];
+                    sid[k] = o.y;
+                    ld_transform(p.xf + (o.x - p.transformIdBase), ps[k], qt[k]);
                 }
-                inMask |= (in ? 1u : 0u) << k; actMask |= (act ? 1u : 0u) << k; vpMask |= (vprev ? 1u : 0u) << k;
+                actMask = inMask = (1u << ITEMS) - 1u;
+            } else {
+                actMask = 0u; inMask = 0u;
+#pragma unroll
+                for (int k = 0; k < ITEMS; ++k) {
+                    const bool in = localBase + uint32_t(k) * 32u < left;
+                    const uint2 o = ob[k * 32];
+                    const bool act = (PASS == PASS_EARLY) ? (in && vr[k * 32] != 0u) : in;             // InitialDrawCull.comp.glsl:21-24
+                    sid[k] = in ? o.y : 0u;                                                    // the ragged tail of the ring holds stale words
+                    if (act) ld_transform(p.xf + (o.x - p.transformIdBase), ps[k], qt[k]);
+                    inMask |= (in ? 1u : 0u) << k; actMask |= (act ? 1u : 0u) << k;
+                }
             }
+            if (VIS_BITS && lane < uint32_t(ITEMS)) s_visPrev[mm & 1u][warp * uint32_t(ITEMS) + lane] = vr[lane];
         }
         if (valid) {
             __syncwarp();
@@ -320,9 +328,11 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
                 uint32_t res = 0u, local = 0u;
                 if (e < qn) {
                     const uint4 a = queue[2u * e], b = queue[2u * e + 1u];
-                    local = b.y & 0xFFFFu;
+                    local = b.y;
+                    bool vp = false;
+                    if (PASS == PASS_LATE) { const uint32_t r = local - warp * uint32_t(WSPAN); vp = ((s_visPrev[ju & 1u][warp * uint32_t(ITEMS) + (r >> 5)] >> (r & 31u)) & 1u) != 0u; }
                     res = eval_entry<PASS, HIZ>(make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w)),
-                                                make_uint2(b.x, b.y), b.z, surfT, lodT, p);
+                                                b.x, vp, b.z, surfT, lodT, p);
                 }
                 const uint32_t eb = __ballot_sync(0xFFFFFFFFu, (res & 2u) != 0u);
                 if (res & 2u) reinterpret_cast<uint32_t*>(queue)[8u * (emitRun + uint32_t(__popc(eb & laneLt))) + 7u] = local | ((res >> 2) << kSLocalBits);

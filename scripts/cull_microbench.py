@@ -93,7 +93,7 @@ def main():
             _, tot = ctx.read_count()
             report(f"late_steady/{vname}", ms, mn, n * 48 + tot * 24 + 4, {"survivors": tot, "visible": vis})
         if on("early_" + vname):
-            for mode, mname in ((3, "stream"), (1, "sparse"), (0, "generic")):
+            for mode, mname in ((1, "pipelined"), (0, "streaming")):
                 ctx.set_option("early_mode", mode)
                 ms, mn = timed(lambda: ctx.early(capi.REC_VK24))
                 _, tot = ctx.read_count()
@@ -105,13 +105,13 @@ def main():
                     vv = (rng.random(n) < frac).astype(np.uint32)
                     ctx.write_visibility(vv)
                     nv = int(vv.sum())
-                    for mode, mname in ((3, "stream"), (1, "sparse"), (0, "generic")):
+                    for mode, mname in ((1, "pipelined"), (0, "streaming")):
                         ctx.set_option("early_mode", mode)
                         ms, mn = timed(lambda: ctx.early(capi.REC_VK24))
                         _, tot = ctx.read_count()
                         report(f"early_vis{int(frac * 100)}pct/{mname}", ms, mn, n * 4 + nv * 40 + tot * 24 + 4, {"survivors": tot, "visible_prev": nv})
                 ctx.write_visibility(keep)
-            ctx.set_option("early_mode", 3)
+            ctx.set_option("early_mode", 1)
         if on("pyramid_" + vname):
             ms, mn = timed(lambda: ctx.build_pyramid(variant))
             o = ctx.outputs()

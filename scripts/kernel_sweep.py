@@ -3,7 +3,7 @@
 'k=v,k=v') times frustum+LOD, the steady-state late pass, frame 0 of the late pass and the early pass with CUDA events, and checks
 that draws / counts / visibility are byte-identical to the FIRST option set's (the baseline variant).
 
-    python scripts/kernel_sweep.py --opts "draw_kernel=0;draw_kernel=1,stream_cfg=0;draw_kernel=1,stream_cfg=1"
+    python scripts/kernel_sweep.py --opts "stream_cfg=2;stream_cfg=6;stream_cfg=2,stream_dynamic=0"
 """
 import argparse
 import hashlib
@@ -22,7 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--objects", type=int, default=B.N_OBJECTS)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--opts", default="draw_kernel=0;draw_kernel=1")
+    ap.add_argument("--opts", default="stream_cfg=2;stream_cfg=6")
     ap.add_argument("--cases", default="frustum,late,frame0,early")
     a = ap.parse_args()
     import torch

@@ -1,7 +1,7 @@
 """BASELINE.json configs[1] at FULL size (16 777 216 objects, 1920x1080 depth, the bench workload): the CUDA path against the oracle,
 byte for byte (the multithreaded oracle finishes a frame of this size in well under a second per pass), plus the size-independent
 properties of the domain: ascending ids, count == population of the visibility mask, idempotence of the late pass under a fixed
-view, shard additivity (two half-scene contexts concatenate to the full list), and the same lists from every kernel variant."""
+view, shard additivity (two half-scene contexts concatenate to the full list), and the same lists from every early-pass variant."""
 import hashlib
 import os
 import sys
@@ -75,9 +75,8 @@ def test_two_phase_frame_full_size_against_oracle(workload):
         ctx.early(); _, e2 = ctx.read_count()
         ctx.late(capi.REC_VK24, capi.HIZ_VK); _, l2 = ctx.read_count()
         assert e2 == int(gvis1.sum()) and l2 == 0 and sha(ctx.read_visibility()) == sha(vis1)
-        # every kernel variant produces the same bytes (v4 pipelined kernel, generic early pass, u32 visibility words)
-        ref_e = None
-        for opts in ({"draw_kernel": 1, "early_mode": 3}, {"draw_kernel": 0, "early_mode": 0}, {"draw_kernel": 1, "early_mode": 1, "vis_words": 1}):
+        # every kernel variant produces the same bytes (pipelined / streaming early pass, 1-bit mask / u32 visibility words as the source)
+        for opts in ({"early_mode": 1}, {"early_mode": 0}, {"early_mode": 1, "early_bits": 0, "vis_words": 1}):
             for k, v in opts.items():
                 ctx.set_option(k, v)
             ctx.write_visibility(vis)

@@ -1,6 +1,6 @@
 """Survivor-list pipeline (cull_stream.cu PASS_FRUSTUM with 8-byte records -> cull_list.cu) for indirect instancing and cluster
 expansion: byte-exact against the oracle over the edge cases (nothing / everything visible, overflowing buckets, dispatch capacity
-clamp, many tiles) and identical to the one-shot kernels it replaced (option list_pipeline = 0)."""
+clamp, many tiles, odd tile counts)."""
 import numpy as np
 import pytest
 
@@ -52,8 +52,7 @@ def test_instancing_views(capi, small_scene, vname):
     nl = len(cap)
     with make_ctx(capi, sc, lod_instances=li, bucket_capacity=cap) as ctx:
         ctx.set_view(view)
-        for mode in (1, 0, 1):                               # the pipeline, the one-shot kernel it replaced, the pipeline again (re-armed state)
-            ctx.set_option("list_pipeline", mode)
+        for mode in (0, 1, 2):                               # repeated launches reuse the re-armed state
             ctx.instanced()
             cmds, total = ctx.read_draws(capi.REC_DX32)
             idx, counters = ctx.read_instances(int(cap.sum()))
@@ -91,8 +90,7 @@ def test_cluster_expand_views(capi, small_scene, vname):
     d_exp, d_tot = O.cluster_expand(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, capacity)
     with make_ctx(capi, sc, cluster_dispatch_capacity=capacity, draw_capacity=16) as ctx:
         ctx.set_view(view)
-        for mode in (1, 0, 1):
-            ctx.set_option("list_pipeline", mode)
+        for mode in (0, 1, 2):
             ctx.cluster_expand()
             got, gtot = ctx.read_cluster_dispatch()
             assert gtot == d_tot, (vname, mode)
