@@ -11,7 +11,7 @@ import numpy as np
 from . import types as T
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libblitzen_cull.so")
+LIB_PATH = os.environ.get("BLZ_CULL_LIB") or os.path.join(_PKG, "libblitzen_cull.so")   # BLZ_CULL_LIB: developer override (A/B builds of the same library)
 
 LIST_OPAQUE, LIST_TRANSPARENT, LIST_ONPC = 0, 1, 2
 REC_VK24, REC_DX32 = 0, 1

@@ -24,10 +24,29 @@ struct Sphere { float x, y, z, r; };
 
 // The reference's 32-byte MeshTransform {pos.xyz, scale, orientation} (Resources/renderingResourcesTypes.h:124-129) read as uploaded, with
 // ONE 256-bit load per object (sm_100 LDG.E.256): one request and exactly one 32-byte sector per gathered transform.
+#ifndef BLZ_XF_LOAD
+#define BLZ_XF_LOAD 0
+#endif
 __device__ __forceinline__ void ld_transform(const MeshTransform* p, float4& ps, float4& qt)
 {
+#if BLZ_XF_LOAD == 0
     asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(ps.x), "=f"(ps.y), "=f"(ps.z), "=f"(ps.w), "=f"(qt.x), "=f"(qt.y), "=f"(qt.z), "=f"(qt.w) : "l"(p));
+#elif BLZ_XF_LOAD == 4
+    // "+f": the destination registers are also inputs, so a loop-carried transform keeps ONE set of registers (with "=f" the compiler
+    // merged the loaded and the carried values with moves placed right behind the load, which wait for the data)
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "+f"(ps.x), "+f"(ps.y), "+f"(ps.z), "+f"(ps.w), "+f"(qt.x), "+f"(qt.y), "+f"(qt.z), "+f"(qt.w) : "l"(p));
+#elif BLZ_XF_LOAD == 1
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(ps.x), "=f"(ps.y), "=f"(ps.z), "=f"(ps.w), "=f"(qt.x), "=f"(qt.y), "=f"(qt.z), "=f"(qt.w) : "l"(p));
+#elif BLZ_XF_LOAD == 2
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ps.x), "=f"(ps.y), "=f"(ps.z), "=f"(ps.w) : "l"(p));
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(qt.x), "=f"(qt.y), "=f"(qt.z), "=f"(qt.w) : "l"(p));
+#elif BLZ_XF_LOAD == 3
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(ps.x), "=f"(ps.y), "=f"(ps.z), "=f"(ps.w), "=f"(qt.x), "=f"(qt.y), "=f"(qt.z), "=f"(qt.w) : "l"(p));
+#endif
 }
 
 // view-space bounding sphere: center = RotateQuat(bc, q) * scale + pos; center = (view * vec4(center, 1)).xyz; radius = br * scale

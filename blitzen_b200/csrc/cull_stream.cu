@@ -295,28 +295,21 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
             const uint2* ob = objRing + stage * TILE + localBase;
             const uint32_t* vr = visRing + stage * VIS_STAGE_WORDS + (VIS_WORDS ? localBase : warp * uint32_t(ITEMS));
             const uint32_t left = p.n - nextTile * uint32_t(TILE);         // objects from the tile's first to the end of the list (>= 1)
-            if (PASS != PASS_EARLY && left >= uint32_t(TILE)) {
-                // a full tile (all but the last one): every item is in range and active -- per object one 64-bit shared load, one subtract,
-                // one address and one 256-bit gather, no predicates and no mask bookkeeping
+            // ONE code path with PREDICATED loads: a predicated load keeps its destination registers tied to the carried values; an
+            // unpredicated copy of the loads behind a "whole tile in range" branch made the compiler merge the two paths with register
+            // moves placed right behind the loads, which wait for the data (measured: +9 % time, long-scoreboard stalls doubled)
+            actMask = 0u; inMask = 0u;
 #pragma unroll
-                for (int k = 0; k < ITEMS; ++k) {
-                    const uint2 o = ob[k * 32];
-                    sid[k] = o.y;
-                    ld_transform(p.xf + (o.x - p.transformIdBase), ps[k], qt[k]);
-                }
-                actMask = inMask = (1u << ITEMS) - 1u;
-            } else {
-                actMask = 0u; inMask = 0u;
-#pragma unroll
-                for (int k = 0; k < ITEMS; ++k) {
-                    const bool in = localBase + uint32_t(k) * 32u < left;
-                    const uint2 o = ob[k * 32];
-                    const bool act = (PASS == PASS_EARLY) ? (in && vr[k * 32] != 0u) : in;             // InitialDrawCull.comp.glsl:21-24
-                    sid[k] = in ? o.y : 0u;                                                    // the ragged tail of the ring holds stale words
-                    if (act) ld_transform(p.xf + (o.x - p.transformIdBase), ps[k], qt[k]);
-                    inMask |= (in ? 1u : 0u) << k; actMask |= (act ? 1u : 0u) << k;
-                }
+            for (int k = 0; k < ITEMS; ++k) {
+                const bool in = localBase + uint32_t(k) * 32u < left;
+                const uint2 o = ob[k * 32];
+                const bool act = (PASS == PASS_EARLY) ? (in && vr[k * 32] != 0u) : in;             // InitialDrawCull.comp.glsl:21-24
+                sid[k] = in ? o.y : 0u;                                                    // the ragged tail of the ring holds stale words
+                if (act) ld_transform(p.xf + (o.x - p.transformIdBase), ps[k], qt[k]);
+                inMask |= (in ? 1u : 0u) << k;
+                if (PASS == PASS_EARLY) actMask |= (act ? 1u : 0u) << k;
             }
+            if (PASS != PASS_EARLY) actMask = inMask;
             if (VIS_BITS && lane < uint32_t(ITEMS)) s_visPrev[mm & 1u][warp * uint32_t(ITEMS) + lane] = vr[lane];
         }
         if (valid) {
@@ -487,6 +480,9 @@ cudaError_t launch_cfg(const DrawCullParams& p, int numSMs, cudaStream_t stream)
 template <int PASS, int HIZ>
 cudaError_t launch_pass(const DrawCullParams& p, int cfg, int numSMs, cudaStream_t stream)
 {
+#ifdef BLZ_STREAM_MINIMAL       // developer A/B builds (scripts/build_variant.sh): one CTA shape, a fraction of the compile time
+    return launch_cfg<PASS, HIZ, 256, 4, 3>(p, numSMs, stream);
+#else
     switch (cfg) {
     case 1: return launch_cfg<PASS, HIZ, 256, 2, 5>(p, numSMs, stream);
     case 2: return launch_cfg<PASS, HIZ, 256, 4, 3>(p, numSMs, stream);
@@ -501,6 +497,7 @@ cudaError_t launch_pass(const DrawCullParams& p, int cfg, int numSMs, cudaStream
     case 11: return launch_cfg<PASS, HIZ, 384, 4, 2>(p, numSMs, stream);
     default: return launch_cfg<PASS, HIZ, 256, 2, 6>(p, numSMs, stream);
     }
+#endif
 }
 
 } // namespace
