@@ -185,7 +185,7 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.transformIdBase = c->transformIdBase;
     p.surfaceCount = c->nSurf; p.lodCount = c->nLods;
     p.recWords = fmt == BLZ_REC_VK24 ? 6u : 8u;
-    p.flags = (flags & kFlagOnpcLodQuirk) | (c->optStreamDynamic ? kFlagDynamicTiles : 0u);
+    p.flags = flags & kFlagOnpcLodQuirk;
     p.capacity = c->drawCap;
     p.view = make_view_consts(c->view);
     p.pyr = c->pyr;
@@ -244,7 +244,7 @@ int run_survivor_list(blz_cull_ctx* c, int list)
     p.transformIdBase = c->transformIdBase;
     p.surfaceCount = c->nSurf; p.lodCount = c->nLods;
     p.recWords = 2u;
-    p.flags = c->optStreamDynamic ? kFlagDynamicTiles : 0u;
+    p.flags = 0u;
     p.capacity = n;
     p.view = make_view_consts(c->view);
     p.pyr = c->pyr;
@@ -742,7 +742,6 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     }
     if (strcmp(name, "early_auto") == 0) { c->optEarlyAuto = value; c->earlyDense = false; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
-    if (strcmp(name, "stream_dynamic") == 0) { c->optStreamDynamic = value; return BLZ_OK; }
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);
 }
 

@@ -50,7 +50,6 @@ struct blz_cull_ctx {
     int64_t optEarlyMode = 1;                 // 1 = pipelined visibility-stream kernel (cull_early.cu), 0 = the streaming kernel (cull_stream.cu, PASS_EARLY) whatever the density
     int64_t optEarlyBits = 1;                 // pipelined early pass streams the 1-bit mask (1) or the 4-B visibility words (0)
     int64_t optVisWords = 0;                  // 1: the streaming late pass also writes the u32-per-object visibility buffer every frame (else on demand)
-    int64_t optStreamDynamic = 1;             // streaming kernel: atomic-ticket tile order (1) or static round-robin (0)
     int64_t optEarlyAuto = 1;                 // early_mode 1: switch to the streaming kernel while more than ~20 % of the objects were visible last frame
     int64_t optStreamCfg = 2;                 // CTA shape of the streaming kernel (see launch_pass in cull_stream.cu)
     uint32_t lastRecWords = 6;                // record width (u32 words) of the pass that last wrote `draws`

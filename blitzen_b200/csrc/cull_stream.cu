@@ -154,7 +154,6 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
     const uint32_t localBase = warp * uint32_t(WSPAN) + lane;           // + 32k = index inside the tile
     const ViewConsts& V = p.view;
     const uint32_t epoch = ld_cg_u32(&p.ctl->epoch) & 0x3FFFFFFFu;      // constant for the whole launch (the last CTA out bumps it)
-    const bool dyn = (p.flags & kFlagDynamicTiles) != 0u;
     const uint32_t cap32 = p.capacity > 0xFFFFFFFFull ? 0xFFFFFFFFu : uint32_t(p.capacity);   // record counts fit 32 bits (n < 2^32)
 
     // ---- carve shared memory --------------------------------------------------------------------------------------------------
@@ -191,34 +190,22 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
         if (VIS_BITS) tma_load_1d(visRing + stage * VIS_STAGE_WORDS, p.visBits + (first >> 5), vb, &s_bar[stage]);
     };
 
-    // Tile order.  STATIC: the CTA's m-th tile is m * gridDim.x + blockIdx.x (all CTAs co-resident: the grid is sized by the
-    // occupancy query); every tile below a CTA's m-th tile is then some CTA's m-th or earlier tile, so the wait for their aggregates
-    // (taken kLagS iterations late) never depends on a LATER step of another CTA.  DYNAMIC (kFlagDynamicTiles): an atomic ticket,
-    // claimed by thread 0 at the top of iteration j for the tile computed in iteration j+2 -- the SAME claim-to-compute delay for
-    // every tile, so tile order follows time order and the lag absorbs the rest.  (Tickets claimed with unequal delays -- two at
-    // once in the prologue -- made a CTA's second tile lower than its neighbour's first and chained the waits through all CTAs:
-    // measured 1-2 ms.)
-    const uint32_t G = gridDim.x;
-    auto tile_of = [&](uint32_t m) -> uint32_t {
-        if (dyn) { const uint32_t t = s_tiles[m & 7u]; return t < p.numTiles ? t : kNoTile; }
-        const uint64_t t = uint64_t(m) * G + blockIdx.x; return t < p.numTiles ? uint32_t(t) : kNoTile;
-    };
+    // Tile order: an atomic ticket, claimed by thread 0 at the top of iteration j for the tile computed in iteration j+2 -- the SAME
+    // claim-to-compute delay for every tile, so tile order follows time order and the lag absorbs the rest.  (Tickets claimed with
+    // unequal delays -- two at once in the prologue -- made a CTA's second tile lower than its neighbour's first and chained the
+    // waits through all CTAs: measured 1-2 ms.  A static round-robin order was kept as a run-time alternative until r02: the kernel
+    // with only this order compiled in needs no spills at 80 registers and is 6.5 % faster.)
+    auto tile_of = [&](uint32_t m) -> uint32_t { const uint32_t t = s_tiles[m & 7u]; return t < p.numTiles ? t : kNoTile; };
     uint32_t lastClaim = 0u;                 // thread 0, dynamic order: the most recent ticket
     if (tid == 0) {
-        if (dyn) { lastClaim = atomicAdd(&p.ctl->ticket, 1u); s_tiles[0] = lastClaim; s_tiles[1] = kNoTile; }
+        lastClaim = atomicAdd(&p.ctl->ticket, 1u); s_tiles[0] = lastClaim; s_tiles[1] = kNoTile;
 #pragma unroll
         for (int s = 0; s < D; ++s) mbar_init(&s_bar[s], 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_sum[0] = s_sum[1] = s_sum[2] = s_sum[3] = 0u;
     }
     __syncthreads();      // barriers initialised, tables visible
-    if (tid == 0) {
-        if (dyn) { if (tile_of(0u) != kNoTile) issue_tile(tile_of(0u), 0u); }
-        else {
-#pragma unroll
-            for (int s = 0; s < D; ++s) if (tile_of(uint32_t(s)) != kNoTile) issue_tile(tile_of(uint32_t(s)), uint32_t(s));
-        }
-    }
+    if (tid == 0 && tile_of(0u) != kNoTile) issue_tile(tile_of(0u), 0u);
 
     // registers carried from the fetch of a tile (iteration j-1) to its arithmetic (iteration j)
     float4 ps[ITEMS], qt[ITEMS];
@@ -240,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
         const bool valid = curTile != kNoTile;                   // uniform over the CTA
         const uint32_t tileBase = curTile * uint32_t(TILE);
         uint32_t ticket = kNoTile;
-        if (dyn && tid == 0 && lastClaim < p.numTiles) { ticket = atomicAdd(&p.ctl->ticket, 1u); lastClaim = ticket; }   // tile of iteration j+2
+        if (tid == 0 && lastClaim < p.numTiles) { ticket = atomicAdd(&p.ctl->ticket, 1u); lastClaim = ticket; }   // tile of iteration j+2
 
         // prefix of tile j-2: this CTA sums the aggregates of every tile between its previous tile and that one -- all threads at
         // once (one L2 round trip however many tiles are in flight), two iterations late (the words are there), and the loads are
@@ -282,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
             }
         }
         const uint32_t inMaskJ = inMask;
-        if (dyn && tid == 0) {       // the ticket is back by now; its ring stage (that of tile j) was consumed before the barrier of iteration j-1
+        if (tid == 0) {       // the ticket is back by now; its ring stage (that of tile j) was consumed before the barrier of iteration j-1
             s_tiles[(mm + 1u) & 7u] = ticket;
             if (ticket < p.numTiles) issue_tile(ticket, (mm + 1u) % uint32_t(D));
         }
@@ -377,11 +364,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
         }
         __syncthreads();      // (B) warp counts of tile j, aggregate sum for tile j-2 visible; ring stage of tile j+1 consumed
 
-        // ---- S4: refill the ring; place tile j's descriptors + publish its aggregate; write out the records of tile j-2 ------------------
-        if (!dyn && tid == 0) {
-            const uint32_t refill = tile_of(mm + uint32_t(D));
-            if (refill != kNoTile) issue_tile(refill, mm % uint32_t(D));
-        }
+        // ---- S4: place tile j's descriptors + publish its aggregate; write out the records of tile j-2 ------------------------------------
         if (valid) {
             uint32_t warpOff = 0u, total = 0u;
 #pragma unroll
@@ -484,18 +467,10 @@ cudaError_t launch_pass(const DrawCullParams& p, int cfg, int numSMs, cudaStream
     return launch_cfg<PASS, HIZ, 256, 4, 3>(p, numSMs, stream);
 #else
     switch (cfg) {
-    case 1: return launch_cfg<PASS, HIZ, 256, 2, 5>(p, numSMs, stream);
-    case 2: return launch_cfg<PASS, HIZ, 256, 4, 3>(p, numSMs, stream);
-    case 3: return launch_cfg<PASS, HIZ, 512, 2, 3>(p, numSMs, stream);
-    case 4: return launch_cfg<PASS, HIZ, 128, 4, 6>(p, numSMs, stream);
-    case 5: return launch_cfg<PASS, HIZ, 512, 2, 2>(p, numSMs, stream);
+    case 3: return launch_cfg<PASS, HIZ, 224, 4, 3>(p, numSMs, stream);       // 7 warps: 96 registers per thread at 3 CTAs / SM
+    case 4: return launch_cfg<PASS, HIZ, 192, 4, 4>(p, numSMs, stream);
     case 6: return launch_cfg<PASS, HIZ, 256, 3, 4>(p, numSMs, stream);
-    case 7: return launch_cfg<PASS, HIZ, 512, 3, 2>(p, numSMs, stream);
-    case 8: return launch_cfg<PASS, HIZ, 128, 4, 7>(p, numSMs, stream);
-    case 9: return launch_cfg<PASS, HIZ, 256, 5, 2>(p, numSMs, stream);
-    case 10: return launch_cfg<PASS, HIZ, 256, 6, 2>(p, numSMs, stream);
-    case 11: return launch_cfg<PASS, HIZ, 384, 4, 2>(p, numSMs, stream);
-    default: return launch_cfg<PASS, HIZ, 256, 2, 6>(p, numSMs, stream);
+    default: return launch_cfg<PASS, HIZ, 256, 4, 3>(p, numSMs, stream);      // cfg 2
     }
 #endif
 }

@@ -52,6 +52,5 @@ enum Pass { PASS_FRUSTUM = 0, PASS_EARLY = 1, PASS_LATE = 2, PASS_TEMPORAL = 3 }
 enum Hiz { HIZ_VK = 0, HIZ_DX = 1, HIZ_NONE = 2 };
 
 constexpr uint32_t kFlagOnpcLodQuirk = 1u;
-constexpr uint32_t kFlagDynamicTiles = 2u;      // streaming cull kernel: atomic-ticket tile order instead of static round-robin
 
 } // namespace blz

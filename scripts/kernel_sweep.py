@@ -3,7 +3,7 @@
 'k=v,k=v') times frustum+LOD, the steady-state late pass, frame 0 of the late pass and the early pass with CUDA events, and checks
 that draws / counts / visibility are byte-identical to the FIRST option set's (the baseline variant).
 
-    python scripts/kernel_sweep.py --opts "stream_cfg=2;stream_cfg=6;stream_cfg=2,stream_dynamic=0"
+    python scripts/kernel_sweep.py --opts "stream_cfg=2;stream_cfg=3;stream_cfg=6"
 """
 import argparse
 import hashlib
@@ -100,6 +100,7 @@ def main():
         if base is None:
             base = sig
             out["survivors"] = {k: v[1] for k, v in sig.items() if isinstance(v, tuple)}
+        out["sig"] = hashlib.sha256(json.dumps(sig, sort_keys=True).encode()).hexdigest()[:12]
         out["identical_to_first"] = (sig == base)
         if sig != base:
             out["diff"] = {k: (sig[k], base[k]) for k in sig if sig[k] != base[k]}
