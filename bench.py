@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="objects in the cpu_baseline sample (0 = the whole workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the extra device timings of the late kernel's other output regimes")
     ap.add_argument("--hiz", default="vk", choices=["vk", "dx"])
     return ap.parse_args()
 
@@ -293,6 +294,45 @@ def main():
     pyr_texels = sum(max(1, o.pyramid_width >> i) * max(1, o.pyramid_height >> i) for i in range(o.pyramid_mips))
 
     peak, peak_src = load_peaks()
+
+    # ---- the same late kernel in its other output regimes (device-timed, NOT part of the step): frame 0 (every frustum survivor is
+    #      emitted) and an all-visible frustum pass (the output-bound end).  Reported as fractions of the same peak. ------------------
+    regimes = None
+    if world == 1 and not args.no_regimes:
+        from blitzen_b200 import scene as _scene
+
+        def timed(fn, prep=None, iters=10):
+            ts = []
+            for it in range(iters + 2):
+                if prep:
+                    prep()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                with torch.cuda.stream(stream):
+                    e0.record(stream); fn(); e1.record(stream)
+                torch.cuda.synchronize()
+                if it >= 2:
+                    ts.append(e0.elapsed_time(e1))
+            return float(np.mean(ts))
+
+        vis_keep = ctx.read_visibility().copy()
+
+        def prep0():
+            ctx.reset_visibility(); ctx.clear_pyramid(variant, DEPTH_W, DEPTH_H)
+        ms0 = timed(lambda: ctx.late(capi.REC_VK24, variant), prep0)
+        _, tot0 = ctx.read_count()
+        cube = _scene.cube_side(args.objects)
+        ctx.set_view(_scene.make_view((cube / 2, cube / 2, -4.0 * cube), z_far=1e9, width=DEPTH_W, height=DEPTH_H))
+        msa = timed(lambda: ctx.frustum_lod())
+        _, tota = ctx.read_count()
+        ctx.set_view(w["view"])
+        msf = timed(lambda: ctx.frustum_lod())
+        _, totf = ctx.read_count()
+        ctx.build_pyramid(variant); ctx.write_visibility(vis_keep)
+        frac = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9 / peak
+        regimes = {"late_frame0": {"ms": ms0, "survivors": int(tot0), "frac": frac(n * 48 + tot0 * 24 + 4, ms0)},
+                   "frustum_lod_bench_view": {"ms": msf, "survivors": int(totf), "frac": frac(n * 40 + totf * 24 + 4, msf)},
+                   "frustum_lod_all_visible": {"ms": msa, "survivors": int(tota), "frac": frac(n * 40 + tota * 24 + 4, msa)}}
+
     b_early, b_late = algorithmic_bytes(n, vis_prev, early_total, late_total)
     b_pyr = pyramid_bytes(DEPTH_W, DEPTH_H, pyr_texels)
     late_gbs = b_late / (t_late * 1e-3) / 1e9
@@ -388,6 +428,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on the host cores -----------------------------------------------
     cpu = None
+    census = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O
@@ -401,6 +442,13 @@ def main():
                 ts.append(dt)
         cpu = {"value": ns / float(np.median(ts)), "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{ns} of {n} objects, early + pyramid + late per step, median of 3 after 1 warm-up, oracle/cull_oracle.cpp with {threads} std::threads"}
+        # north_star: objects within epsilon of a frustum plane / Hi-Z texel or level boundary "are counted and reported".  These are the
+        # only objects on which a real GLSL/HLSL GPU (FMA contraction, 8-bit sampler weights) may legitimately differ from the oracle;
+        # the CUDA path itself is bit-exact against the oracle on all of them (tests/).
+        hv = 0 if args.hiz == "vk" else 1
+        cen = O.boundary_census(w["objs"][:ns], w["transforms"], w["surfaces"], w["lods"], w["view"], O.build_pyramid(w["depth"], hv, threads=threads), hv,
+                                ulp_tol=4.0, texel_tol=1.0 / 256.0, transform_id_base=w["transform_id_base"], threads=threads)
+        census = dict(cen, objects=int(ns), eps_plane_ulp=4.0, eps_texel=1.0 / 256.0)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -408,7 +456,7 @@ def main():
                 "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_frame": e2e_frame, "gpu_launches": int(launches),
                 "clocks": clocks,
                 "detail": {"visible_prev_frame": vis_prev, "early_draws": early_total, "late_draws": late_total, "early_list_checksum": early_checksum,
-                           "kernel_ms": {"early": t_early, "pyramid": t_pyr, "late": t_late}}}
+                           "kernel_ms": {"early": t_early, "pyramid": t_pyr, "late": t_late}, "late_kernel_regimes": regimes, "boundary_census": census}}
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist is not None:

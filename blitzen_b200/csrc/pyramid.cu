@@ -20,6 +20,7 @@ namespace {
 
 constexpr int kPyrThreads = 256;
 constexpr int kPyrTile = 32;
+constexpr int kPyrMinBlocks = 8;                     // 8 x 148 = 1184 resident CTAs: the 1024 tiles of a 1080p build are ONE wave (at 6 per SM they were 1.15)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
@@ -84,7 +85,7 @@ __device__ __forceinline__ float tail_texel(const float* src, uint32_t sw, uint3
 }
 
 template <int VARIANT, bool USE_TMA>
-__global__ void __launch_bounds__(kPyrThreads) pyramid_kernel(const __grid_constant__ PyramidBuildParams p, const __grid_constant__ CUtensorMap tmap)
+__global__ void __launch_bounds__(kPyrThreads, kPyrMinBlocks) pyramid_kernel(const __grid_constant__ PyramidBuildParams p, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -167,9 +168,11 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_kernel(const __grid_const
     if (p.tileLevels >= p.mips) {
         return;
     }
-    __threadfence();
+    // release of this CTA's mip texels: CTA barrier, then ONE thread fences (cumulative) and takes the ticket.  (A __threadfence() in
+    // every thread was 11 % of the kernel's stall samples: profiles/r02c_pyramid_*.)
     __syncthreads();
     if (tid == 0) {
+        __threadfence();
         const uint32_t t = atomicAdd(p.ticket, 1u);
         s_last = (t == gridDim.x * gridDim.y - 1u) ? 1u : 0u;
         if (s_last) *p.ticket = 0u;                                  // re-arm for the next build on this stream

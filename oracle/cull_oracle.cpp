@@ -32,6 +32,7 @@
 #include <cstdint>
 #include <cstring>
 #include <cmath>
+#include <array>
 #include <vector>
 #include <thread>
 #include <algorithm>
@@ -546,16 +547,18 @@ int oracle_cluster_cull(const oracle_scene* sc, const void* view, const oracle_p
 //   out[1] = frustum-visible objects whose Hi-Z sample coordinate is within texelTol of a texel-centre line (weight -> 0)
 //   out[2] = frustum-visible objects whose max(w,h) is within ulpTol ulps of a power of two (mip level boundary)
 //   out[3] = frustum-visible objects whose depthSphere is within ulpTol ulps of the sampled depth
-int oracle_boundary_census(const oracle_scene* sc, const void* view, const oracle_pyramid* pyr, int hiz, float ulpTol, float texelTol, uint64_t* out)
+int oracle_boundary_census(const oracle_scene* sc, const void* view, const oracle_pyramid* pyr, int hiz, float ulpTol, float texelTol, uint64_t* out, int threads)
 {
     Scene S{ (const RenderObject*)sc->objs, sc->nObj, (const MeshTransform*)sc->transforms, (const PrimitiveSurface*)sc->surfaces,
              (const LodData*)sc->lods, (const Cluster*)sc->clusters, sc->objectIdBase };
     ViewData V; std::memcpy(&V, view, sizeof(V));
     Pyramid P{}; if (pyr) { P.data = pyr->data; P.width = pyr->width; P.height = pyr->height; P.mips = pyr->mips; std::memcpy(P.offset, pyr->offset, sizeof(P.offset)); }
-    out[0] = out[1] = out[2] = out[3] = 0;
     const float eps = 1.1920929e-7f * ulpTol;
     auto near = [&](float a, float b) { float m = std::fmax(std::fabs(a), std::fabs(b)); return std::fabs(a - b) <= eps * m; };
-    for (uint32_t i = 0; i < S.nObj; ++i) {
+    std::vector<std::array<uint64_t, 4>> part(size_t(threads > 1 ? threads : 1), std::array<uint64_t, 4>{ 0, 0, 0, 0 });
+    parallel_ranges(S.nObj, threads, [&](int t, uint64_t ra, uint64_t rb) {
+    uint64_t* out = part[size_t(t)].data();
+    for (uint64_t i = ra; i < rb; ++i) {
         RenderObject obj = S.objs[i];
         const MeshTransform& T = S.xf[obj.transformId];
         const PrimitiveSurface& sf = S.surf[obj.surfaceId];
@@ -595,6 +598,9 @@ int oracle_boundary_census(const oracle_scene* sc, const void* view, const oracl
         }
         if (near(V.zNear / (c.z - r), depth)) out[3]++;
     }
+    });
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (auto& q : part) for (int k = 0; k < 4; ++k) out[k] += q[size_t(k)];
     return 0;
 }
 

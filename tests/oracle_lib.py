@@ -166,12 +166,12 @@ def cluster_cull(objs, transforms, surfaces, lods, clusters, view, dispatch, mod
     return out[:written.value], total.value
 
 
-def boundary_census(objs, transforms, surfaces, lods, view, pyramid, hiz, ulp_tol=4.0, texel_tol=1.0 / 256.0, transform_id_base=0):
+def boundary_census(objs, transforms, surfaces, lods, view, pyramid, hiz, ulp_tol=4.0, texel_tol=1.0 / 256.0, transform_id_base=0, threads=1):
     s = _scene(objs, transforms, surfaces, lods, None, 0, transform_id_base)
     v = np.ascontiguousarray(view_with_pyramid(view, pyramid))
     out = (C.c_uint64 * 4)()
     pyr_c = pyramid.c() if pyramid is not None else None
-    lib().oracle_boundary_census(C.byref(s), _p(v), C.byref(pyr_c) if pyr_c is not None else None, C.c_int(hiz), C.c_float(ulp_tol), C.c_float(texel_tol), out)
+    lib().oracle_boundary_census(C.byref(s), _p(v), C.byref(pyr_c) if pyr_c is not None else None, C.c_int(hiz), C.c_float(ulp_tol), C.c_float(texel_tol), out, C.c_int(threads))
     return {"near_frustum_plane": int(out[0]), "near_texel_boundary": int(out[1]), "near_mip_boundary": int(out[2]), "near_depth_equal": int(out[3])}
 
 
