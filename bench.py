@@ -376,11 +376,11 @@ def main():
             ctx.set_depth(depth_v)
             ctx.early(capi.REC_VK24)
             wv, tv = C.c_uint32(), C.c_uint32()
-            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, C.c_void_p(draws_v.ctypes.data), n, C.byref(wv), C.byref(tv)))
+            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, capi.REC_VK24, C.c_void_p(draws_v.ctypes.data), n, C.byref(wv), C.byref(tv)))
             ctx.build_pyramid(variant)
             ctx.late(capi.REC_VK24, variant)
             wl, tl = C.c_uint32(), C.c_uint32()
-            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, C.c_void_p(draws_v.ctypes.data), n, C.byref(wl), C.byref(tl)))
+            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, capi.REC_VK24, C.c_void_p(draws_v.ctypes.data), n, C.byref(wl), C.byref(tl)))
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             d2h = (wv.value + wl.value) * 24 + 16
@@ -408,11 +408,11 @@ def main():
             ctx.set_view(w["view"])
             ctx.early(capi.REC_VK24)
             wv, tv = C.c_uint32(), C.c_uint32()
-            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, C.c_void_p(draws_v.ctypes.data), n, C.byref(wv), C.byref(tv)))
+            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, capi.REC_VK24, C.c_void_p(draws_v.ctypes.data), n, C.byref(wv), C.byref(tv)))
             ctx.build_pyramid(variant)
             ctx.late(capi.REC_VK24, variant)
             wl, tl = C.c_uint32(), C.c_uint32()
-            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, C.c_void_p(draws_v.ctypes.data), n, C.byref(wl), C.byref(tl)))
+            ctx._check(ctx._lib.blz_cull_read_draws(ctx._h, capi.REC_VK24, C.c_void_p(draws_v.ctypes.data), n, C.byref(wl), C.byref(tl)))
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if it >= 2:

@@ -48,6 +48,11 @@ class ConsumeSummary(C.Structure):
                 ("bad_object", C.c_uint32), ("bad_lod", C.c_uint32), ("unsorted", C.c_uint32), ("pad", C.c_uint32), ("lod_hist", C.c_uint32 * 256)]
 
 
+class ExportedOutputs(C.Structure):
+    _fields_ = [("draws_fd", C.c_int), ("counts_fd", C.c_int), ("draws_alloc_bytes", C.c_uint64), ("counts_alloc_bytes", C.c_uint64),
+                ("draw_capacity_records", C.c_uint64), ("count_offset_bytes", C.c_uint64), ("generation", C.c_uint32), ("pad", C.c_uint32)]
+
+
 class Outputs(C.Structure):
     _fields_ = [
         ("draws", C.c_void_p), ("draw_count", C.c_void_p), ("visibility", C.c_void_p),
@@ -71,6 +76,8 @@ ABI_SYMBOLS = [
     "blz_cull_read_visibility", "blz_cull_read_cluster_dispatch", "blz_cull_read_instances", "blz_cull_read_pyramid",
     "blz_cull_gather_export", "blz_cull_gather_import", "blz_cull_gather_configure", "blz_cull_gather_push", "blz_cull_gather_push_async", "blz_cull_gather_join",
     "blz_cull_gather_read", "blz_cull_gather_outputs", "blz_cull_instances_export", "blz_cull_instances_import", "blz_cull_instances_push", "blz_cull_instances_counts", "blz_cull_consume_draws", "blz_cull_consume_instances", "blz_cull_launch_count", "blz_cull_set_option",
+    "blz_cull_export_outputs", "blz_cull_export_fence", "blz_cull_signal_fence", "blz_cull_import_semaphore", "blz_cull_signal_semaphore",
+    "blz_interop_import", "blz_interop_release", "blz_interop_wait_fence", "blz_interop_read",
 ]
 
 _lib = None
@@ -97,7 +104,7 @@ def load_library():
         "blz_cull_temporal": [vp, i, i, i], "blz_cull_instanced": [vp, i], "blz_cull_cluster_expand": [vp, i],
         "blz_cull_cluster_cull": [vp, i, i, i], "blz_cull_set_cluster_dispatch": [vp, vp, u64, i],
         "blz_cull_get_outputs": [vp, C.POINTER(Outputs)],
-        "blz_cull_read_draws": [vp, vp, u64, C.POINTER(u32), C.POINTER(u32)],
+        "blz_cull_read_draws": [vp, i, vp, u64, C.POINTER(u32), C.POINTER(u32)],
         "blz_cull_read_count": [vp, C.POINTER(u32), C.POINTER(u32)], "blz_cull_read_visibility": [vp, vp],
         "blz_cull_read_cluster_dispatch": [vp, vp, u64, C.POINTER(u32), C.POINTER(u32)],
         "blz_cull_read_instances": [vp, vp, u64, vp], "blz_cull_read_pyramid": [vp, vp, u64, vp, vp],
@@ -107,6 +114,10 @@ def load_library():
         "blz_cull_instances_export": [vp, vp], "blz_cull_instances_import": [vp, vp, i, i], "blz_cull_instances_push": [vp, vp, vp, vp], "blz_cull_instances_counts": [vp, vp],
         "blz_cull_consume_draws": [vp, i, i, vp], "blz_cull_consume_instances": [vp, i, vp],
         "blz_cull_launch_count": [vp, C.POINTER(u64)], "blz_cull_set_option": [vp, C.c_char_p, C.c_int64],
+        "blz_cull_export_outputs": [vp, C.POINTER(ExportedOutputs)], "blz_cull_export_fence": [vp, vp], "blz_cull_signal_fence": [vp],
+        "blz_cull_import_semaphore": [vp, i, i], "blz_cull_signal_semaphore": [vp, u64],
+        "blz_interop_import": [i, i, u64, C.POINTER(vp)], "blz_interop_release": [vp, u64], "blz_interop_wait_fence": [vp, vp],
+        "blz_interop_read": [vp, vp, u64, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -145,6 +156,7 @@ class CullContext:
         self.n_objects = 0
         self.n_lods = 0
         self._keep = []
+        self._last_fmt = REC_VK24
         # A/B knobs for measurements (bench.py / profiling scripts), e.g. BLZ_OPTIONS="cull_items=4,pyramid_tma=0"
         for kv in filter(None, os.environ.get("BLZ_OPTIONS", "").split(",")):
             k, v = kv.split("=")
@@ -245,24 +257,30 @@ class CullContext:
     # ---- passes ----------------------------------------------------------------------------------------------------
     def frustum_lod(self, list_id=LIST_OPAQUE, fmt=REC_VK24, flags=0):
         self._check(self._lib.blz_cull_frustum_lod(self._h, list_id, fmt, flags))
+        self._last_fmt = fmt
 
     def early(self, fmt=REC_VK24):
         self._check(self._lib.blz_cull_early(self._h, fmt))
+        self._last_fmt = fmt
 
     def late(self, fmt=REC_VK24, hiz=HIZ_VK):
         self._check(self._lib.blz_cull_late(self._h, fmt, hiz))
+        self._last_fmt = fmt
 
     def temporal(self, list_id=LIST_OPAQUE, fmt=REC_VK24, hiz=HIZ_VK):
         self._check(self._lib.blz_cull_temporal(self._h, list_id, fmt, hiz))
+        self._last_fmt = fmt
 
     def instanced(self, list_id=LIST_OPAQUE):
         self._check(self._lib.blz_cull_instanced(self._h, list_id))
+        self._last_fmt = REC_DX32
 
     def cluster_expand(self, list_id=LIST_OPAQUE):
         self._check(self._lib.blz_cull_cluster_expand(self._h, list_id))
 
     def cluster_cull(self, mode=CLUSTER_PASSTHROUGH, fmt=REC_VK24, hiz=HIZ_VK):
         self._check(self._lib.blz_cull_cluster_cull(self._h, mode, fmt, hiz))
+        self._last_fmt = fmt
 
     def set_cluster_dispatch(self, records):
         records = _as(records, T.ClusterDispatchData)
@@ -279,13 +297,16 @@ class CullContext:
         self._check(self._lib.blz_cull_read_count(self._h, C.byref(w), C.byref(t)))
         return w.value, t.value
 
-    def read_draws(self, fmt=REC_VK24, capacity=None):
-        """Returns (records, total): records is a structured array of the `written` records."""
+    def read_draws(self, fmt=None, capacity=None):
+        """Returns (records, total): records is a structured array of the `written` records.  fmt defaults to the format of the pass
+        this object ran last; the library refuses a format other than the one the last pass wrote (the buffer sizes differ)."""
+        if fmt is None:
+            fmt = self._last_fmt
         w, t = self.read_count()
         n = w if capacity is None else min(w, capacity)
         out = np.zeros(n, dtype=REC_DTYPE[fmt])
         w2, t2 = C.c_uint32(), C.c_uint32()
-        self._check(self._lib.blz_cull_read_draws(self._h, _ptr(out) if n else None, n, C.byref(w2), C.byref(t2)))
+        self._check(self._lib.blz_cull_read_draws(self._h, int(fmt), _ptr(out) if n else None, n, C.byref(w2), C.byref(t2)))
         return out, t2.value
 
     def read_visibility(self):
@@ -376,6 +397,21 @@ class CullContext:
         v = C.c_uint64()
         self._check(self._lib.blz_cull_launch_count(self._h, C.byref(v)))
         return v.value
+
+    # ---- zero-copy export of the outputs (csrc/interop.cu) --------------------------------------------------------------
+    def export_outputs(self):
+        """Moves draws / counts into exportable allocations and returns an ExportedOutputs (file descriptors owned by the caller)."""
+        e = ExportedOutputs()
+        self._check(self._lib.blz_cull_export_outputs(self._h, C.byref(e)))
+        return e
+
+    def export_fence(self):
+        h = (C.c_ubyte * 64)()
+        self._check(self._lib.blz_cull_export_fence(self._h, h))
+        return bytes(h)
+
+    def signal_fence(self):
+        self._check(self._lib.blz_cull_signal_fence(self._h))
 
     def set_option(self, name, value):
         self._check(self._lib.blz_cull_set_option(self._h, name.encode(), int(value)))

@@ -12,7 +12,7 @@
 #include <vector>
 #include <new>
 
-namespace blz { void pyramid_plan(PyramidBuildParams& p); void gather_release(blz_cull_ctx* c); }
+namespace blz { void pyramid_plan(PyramidBuildParams& p); void gather_release(blz_cull_ctx* c); void interop_release(blz_cull_ctx* c); }
 using namespace blz;
 
 namespace {
@@ -298,6 +298,7 @@ static void free_scene(blz_cull_ctx* c)
     for (int i = 0; i < 3; ++i) { dfree(c->objs[i]); c->nObjs[i] = 0; }
     dfree(c->xf); c->nXf = 0;
     dfree(c->surf); dfree(c->lods); dfree(c->clusters); dfree(c->lodInst); dfree(c->bucketCap);
+    if (c->expDraws.active) { blz::exportable_free(c->expDraws); c->draws = nullptr; }
     dfree(c->vis); dfree(c->visBits); dfree(c->draws); dfree(c->drawsAlt); dfree(c->dispatch); dfree(c->instIdx); dfree(c->survList); dfree(c->listScratch); c->capSurvList = 0; c->capListScratch = 0;
     c->capVisBits = 0; c->visBitsValid = false;
     c->nSurf = c->nLods = c->nClusters = c->nLodInst = 0; c->drawCap = c->dispatchCap = c->instCap = 0;
@@ -314,6 +315,8 @@ int blz_cull_destroy(blz_cull_ctx* c)
     if (c->gatherStream) cudaStreamSynchronize(c->gatherStream);
     free_scene(c);
     if (c->visTotalHost) { cudaFreeHost(c->visTotalHost); c->visTotalHost = nullptr; }
+    if (c->expCounts.active) { blz::exportable_free(c->expCounts); c->counts = nullptr; }
+    blz::interop_release(c);
     dfree(c->ctl); dfree(c->status); dfree(c->counts); dfree(c->depthOwned); dfree(c->pyrData); dfree(c->pyrTicket);
     blz::gather_release(c);
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
@@ -394,7 +397,18 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     {
         if (c->gatherStream) CU_TRY(cudaStreamSynchronize(c->gatherStream));
         const size_t before = c->capDraws;
-        TRY_RC(grow(c, c->draws, c->capDraws, size_t(c->drawCap) * 8u * sizeof(uint32_t)));
+        const size_t need = size_t(c->drawCap) * 8u * sizeof(uint32_t);
+        if (c->expDraws.active) {
+            // exported outputs stay exportable: a buffer that has to grow is re-created the same way (blz_cull_export_outputs again)
+            if (c->expDraws.size < need) {
+                CU_TRY(cudaStreamSynchronize(c->stream));
+                blz::exportable_free(c->expDraws); c->draws = nullptr; c->capDraws = 0;
+                TRY_RC(blz::exportable_alloc(c->device, need, c->expDraws));
+                c->draws = static_cast<uint32_t*>(c->expDraws.ptr); c->capDraws = c->expDraws.size;
+                c->exportGeneration++;
+            }
+        } else
+        TRY_RC(grow(c, c->draws, c->capDraws, need));
         if (c->capDraws != before && c->drawsAlt) { cudaFree(c->drawsAlt); c->drawsAlt = nullptr; }   // re-created by the next asynchronous push
     }
     c->dispatchCap = d->cluster_dispatch_capacity;
@@ -669,10 +683,14 @@ static int read_records(blz_cull_ctx* c, const uint32_t* dev, const uint32_t* de
     return BLZ_OK;
 }
 
-// capacity_records counts records of the format the last pass wrote (VK24 or DX32)
-int blz_cull_read_draws(blz_cull_ctx* c, void* host, uint64_t cap, uint32_t* written, uint32_t* total)
+// `fmt` is the record layout the caller's buffer is made of; it must be the one the last pass wrote (a DX32 list copied into a buffer
+// sized for VK24 records would overrun it)
+int blz_cull_read_draws(blz_cull_ctx* c, int fmt, void* host, uint64_t cap, uint32_t* written, uint32_t* total)
 {
     if (!c || !c->draws) return fail(BLZ_ERR_INVALID, "no scene uploaded");
+    if (fmt != BLZ_REC_VK24 && fmt != BLZ_REC_DX32) return fail(BLZ_ERR_INVALID, "unknown record format %d", fmt);
+    const uint32_t words = fmt == BLZ_REC_VK24 ? 6u : 8u;
+    if (words != c->lastRecWords) return fail(BLZ_ERR_INVALID, "the last pass wrote %u-byte records, the caller asked for %u-byte records", c->lastRecWords * 4u, words * 4u);
     return read_records(c, c->draws, c->drawCounts, c->lastRecWords, host, cap, written, total);
 }
 

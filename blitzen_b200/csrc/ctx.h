@@ -4,6 +4,13 @@
 #include "cull_kernels.cuh"
 #include <string>
 
+namespace blz {
+// a device allocation made with the virtual memory management API so that it can be exported as a file descriptor (interop.cu)
+struct ExportableBuffer { void* ptr = nullptr; size_t size = 0; uint64_t handle = 0; bool active = false; };
+int exportable_alloc(int device, size_t bytes, ExportableBuffer& b);
+void exportable_free(ExportableBuffer& b);
+}
+
 struct blz_cull_ctx {
     int device = 0, numSMs = 0;
     cudaStream_t stream = nullptr, ownStream = nullptr;
@@ -60,6 +67,9 @@ struct blz_cull_ctx {
     uint32_t* instDst = nullptr; bool instDstMapped = false;   // presenter's instance index buffer (instance-list gather)
     // asynchronous push: the list just pushed stays readable in `drawsAlt` while the next pass writes `draws` (blz_cull_gather_push_async)
     uint32_t* drawsAlt = nullptr; uint32_t lastRecWordsAlt = 6; int drawSlot = 0;
+    // zero-copy export of the outputs (interop.cu): when active, `draws` / `counts` live in these allocations instead of cudaMalloc memory
+    blz::ExportableBuffer expDraws, expCounts; uint32_t exportGeneration = 0;
+    cudaEvent_t exportFence = nullptr; void* extSemaphore = nullptr; bool extSemaphoreTimeline = false;
     cudaStream_t gatherStream = nullptr; cudaEvent_t evCull = nullptr, evPush[2] = { nullptr, nullptr }; bool evPushValid[2] = { false, false };
 };
 

@@ -247,6 +247,7 @@ int blz_cull_gather_push_async(blz_cull_ctx* c, uint32_t epoch)
         CU_TRY(cudaEventCreateWithFlags(&c->evPush[0], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&c->evPush[1], cudaEventDisableTiming));
     }
+    if (c->expDraws.active) return fail(BLZ_ERR_STATE, "asynchronous pushes alternate two draw buffers: not available once the outputs have been exported");
     if (!c->drawsAlt) CU_TRY(cudaMalloc(&c->drawsAlt, c->capDraws));
     CU_TRY(cudaEventRecord(c->evCull, c->stream));
     CU_TRY(cudaStreamWaitEvent(c->gatherStream, c->evCull, 0));

@@ -121,7 +121,7 @@ namespace BlitzenCuda
     void* CudaCullRenderer::IndirectDrawBuffer() const { blz_outputs o; return (m_ctx && blz_cull_get_outputs(m_ctx, &o) == BLZ_OK) ? o.draws : nullptr; }
     uint32_t* CudaCullRenderer::IndirectCountBuffer() const { blz_outputs o; return (m_ctx && blz_cull_get_outputs(m_ctx, &o) == BLZ_OK) ? o.draw_count : nullptr; }
     uint8_t CudaCullRenderer::ReadDrawCount(uint32_t* w, uint32_t* t) { return Check(blz_cull_read_count(m_ctx, w, t), "ReadDrawCount"); }
-    uint8_t CudaCullRenderer::ReadDraws(void* p, uint64_t cap, uint32_t* w, uint32_t* t) { return Check(blz_cull_read_draws(m_ctx, p, cap, w, t), "ReadDraws"); }
+    uint8_t CudaCullRenderer::ReadDraws(void* p, uint64_t cap, uint32_t* w, uint32_t* t) { return Check(blz_cull_read_draws(m_ctx, int(m_format), p, cap, w, t), "ReadDraws"); }
     uint8_t CudaCullRenderer::ReadVisibility(uint32_t* p) { return Check(blz_cull_read_visibility(m_ctx, p), "ReadVisibility"); }
     uint8_t CudaCullRenderer::WaitIdle() { return Check(blz_cull_synchronize(m_ctx), "WaitIdle"); }
 }

@@ -40,7 +40,8 @@ typedef enum blz_status {
     BLZ_ERR_INVALID = -1,      /* bad argument / call order */
     BLZ_ERR_CUDA = -2,         /* CUDA runtime error (no device, launch failure, out of memory) */
     BLZ_ERR_CAPACITY = -3,     /* a fixed internal capacity would be exceeded (tables too large, ...) */
-    BLZ_ERR_UNSUPPORTED = -4
+    BLZ_ERR_UNSUPPORTED = -4,
+    BLZ_ERR_STATE = -5         /* the call needs something an earlier call sets up (scene, export, fence) */
 } blz_status;
 
 /* which render-object list a pass runs over: the reference keeps three (Resources/RenderObject/blitRender.h:14-21) and
@@ -171,7 +172,8 @@ int blz_cull_set_cluster_dispatch(blz_cull_ctx* ctx, const void* records, uint64
 /* ---- outputs -------------------------------------------------------------------------------------------------------- */
 int blz_cull_get_outputs(blz_cull_ctx* ctx, blz_outputs* out);
 /* synchronising read-backs (tests, CPU consumers).  Any pointer may be NULL. */
-int blz_cull_read_draws(blz_cull_ctx* ctx, void* records_host, uint64_t capacity_records, uint32_t* out_written, uint32_t* out_total);
+/* record_format = the layout `records_host` is made of; BLZ_ERR_INVALID when the last pass wrote the other one (indirect instancing writes DX32) */
+int blz_cull_read_draws(blz_cull_ctx* ctx, int record_format, void* records_host, uint64_t capacity_records, uint32_t* out_written, uint32_t* out_total);
 int blz_cull_read_count(blz_cull_ctx* ctx, uint32_t* out_written, uint32_t* out_total);
 int blz_cull_read_visibility(blz_cull_ctx* ctx, uint32_t* visibility_host);
 int blz_cull_read_cluster_dispatch(blz_cull_ctx* ctx, void* records_host, uint64_t capacity_records, uint32_t* out_written, uint32_t* out_total);
@@ -220,6 +222,37 @@ int blz_cull_instances_import(blz_cull_ctx* ctx, const void* presenter_blob64 /*
 int blz_cull_instances_counts(blz_cull_ctx* ctx, uint32_t* dst_device /* lod_count words, stream-ordered */);
 int blz_cull_instances_push(blz_cull_ctx* ctx, const uint32_t* all_counts_device /* [world][lod_count] */, const uint32_t* global_offset_device, const uint32_t* global_cap_device);
 int blz_cull_gather_outputs(blz_cull_ctx* ctx, void** out_records_device, uint32_t** out_flags_device);
+
+/* ---- zero-copy hand-over of the outputs --------------------------------------------------------------------
+ * Replaces: the renderer reading `indirectDrawBuffer` / `indirectCountBuffer` in vkCmdDrawIndexedIndirectCount
+ * (BlitzenVulkan/vulkanDraw.cpp:469-471; buffers created in vulkanRendererSetup.cpp:365-666).  The draw-record buffer and the count
+ * block are moved into exportable allocations and handed out as POSIX file descriptors (one per allocation, owned by the caller):
+ *   Vulkan : VkImportMemoryFdInfoKHR{handleType = VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT, fd}, allocationSize = *_alloc_bytes,
+ *            bind to a VkBuffer with INDIRECT_BUFFER usage; the draw reads records at offset 4, stride 24 (VK24) and the count at
+ *            count_offset_bytes (INTEGRATION.md shows the snippet)
+ *   CUDA   : blz_interop_import below (cuMemImportFromShareableHandle + map)
+ * Call after blz_cull_upload_scene; a later upload that has to GROW the draw buffer re-allocates it (still exportable) and bumps
+ * `generation`: export again.  Not available together with blz_cull_gather_push_async (which alternates two draw buffers). */
+typedef struct blz_exported_outputs {
+    int draws_fd, counts_fd;
+    uint64_t draws_alloc_bytes, counts_alloc_bytes;   /* sizes of the two allocations (what the importer must map) */
+    uint64_t draw_capacity_records;                   /* records the buffer holds (32 B reserved per record) */
+    uint64_t count_offset_bytes;                      /* byte offset of {written, total} inside the count block */
+    uint32_t generation, pad;
+} blz_exported_outputs;
+int blz_cull_export_outputs(blz_cull_ctx* ctx, blz_exported_outputs* out);
+/* ordering for CUDA consumers: an interprocess event (64-byte cudaIpcEventHandle_t), recorded on the context's stream by signal_fence */
+int blz_cull_export_fence(blz_cull_ctx* ctx, void* out_ipc_event_handle_64);
+int blz_cull_signal_fence(blz_cull_ctx* ctx);
+/* ordering for the renderer: import the VkSemaphore the renderer exported (vkGetSemaphoreFdKHR; timeline or binary) and signal it on
+ * the context's stream behind the cull passes -- the renderer's draw submission waits on it */
+int blz_cull_import_semaphore(blz_cull_ctx* ctx, int fd, int is_timeline);
+int blz_cull_signal_semaphore(blz_cull_ctx* ctx, uint64_t value);
+/* the consumer's side for CUDA consumers (no context needed): map an exported allocation, order behind the fence, read */
+int blz_interop_import(int cuda_device, int fd, uint64_t alloc_bytes, void** out_device_ptr);
+int blz_interop_release(void* device_ptr, uint64_t alloc_bytes);
+int blz_interop_wait_fence(const void* ipc_event_handle_64, void* cuda_stream);
+int blz_interop_read(void* host_dst, const void* device_src, uint64_t bytes, void* cuda_stream);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------------------ */
 /* number of kernels this library has launched on this context since creation (bench.py's gpu_launches) */
