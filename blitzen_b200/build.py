@@ -16,7 +16,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 
-CUDA_SOURCES = ["capi.cu", "cull_stream.cu", "cull_early.cu", "cull_cluster.cu", "cull_list.cu", "pyramid.cu", "gather.cu", "consume.cu", "interop.cu"]
+CUDA_SOURCES = ["capi.cu", "cull_stream.cu", "cull_early.cu", "cull_cluster.cu", "cull_list.cu", "pyramid.cu", "gather.cu", "consume.cu", "interop.cu", "raster_depth.cu"]
 CUDA_HEADERS = ["ctx.h", "cull_types.cuh", "cull_math.cuh", "cull_kernels.cuh", "scan_lookback.cuh", os.path.join("..", "..", "include", "blz_cull.h")]
 LIB_CULL = os.path.join(PKG, "libblitzen_cull.so")
 LIB_SCENE = os.path.join(PKG, "libblz_scene.so")

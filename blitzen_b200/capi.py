@@ -77,6 +77,7 @@ ABI_SYMBOLS = [
     "blz_cull_gather_export", "blz_cull_gather_import", "blz_cull_gather_configure", "blz_cull_gather_push", "blz_cull_gather_push_async", "blz_cull_gather_join",
     "blz_cull_gather_read", "blz_cull_gather_outputs", "blz_cull_instances_export", "blz_cull_instances_import", "blz_cull_instances_push", "blz_cull_instances_counts", "blz_cull_consume_draws", "blz_cull_consume_instances", "blz_cull_launch_count", "blz_cull_set_option",
     "blz_cull_export_outputs", "blz_cull_export_fence", "blz_cull_signal_fence", "blz_cull_import_semaphore", "blz_cull_signal_semaphore",
+    "blz_cull_raster_depth", "blz_cull_read_depth",
     "blz_interop_import", "blz_interop_release", "blz_interop_wait_fence", "blz_interop_read",
 ]
 
@@ -116,6 +117,7 @@ def load_library():
         "blz_cull_launch_count": [vp, C.POINTER(u64)], "blz_cull_set_option": [vp, C.c_char_p, C.c_int64],
         "blz_cull_export_outputs": [vp, C.POINTER(ExportedOutputs)], "blz_cull_export_fence": [vp, vp], "blz_cull_signal_fence": [vp],
         "blz_cull_import_semaphore": [vp, i, i], "blz_cull_signal_semaphore": [vp, u64],
+        "blz_cull_raster_depth": [vp, i, u32, u32], "blz_cull_read_depth": [vp, vp, u64, vp],
         "blz_interop_import": [i, i, u64, C.POINTER(vp)], "blz_interop_release": [vp, u64], "blz_interop_wait_fence": [vp, vp],
         "blz_interop_read": [vp, vp, u64, vp],
     }
@@ -247,6 +249,17 @@ class CullContext:
 
     def set_depth_device(self, dev_ptr, width, height):
         self._check(self._lib.blz_cull_set_depth_device(self._h, C.c_void_p(dev_ptr), width, height))
+
+    def raster_depth(self, width, height, list_id=LIST_OPAQUE):
+        """Software depth from the current draw list (csrc/raster_depth.cu); becomes the depth image build_pyramid reads."""
+        self._check(self._lib.blz_cull_raster_depth(self._h, list_id, width, height))
+
+    def read_depth(self):
+        wh = (C.c_uint32 * 2)()
+        self._check(self._lib.blz_cull_read_depth(self._h, None, 0, wh))
+        out = np.zeros((wh[1], wh[0]), dtype=np.float32)
+        self._check(self._lib.blz_cull_read_depth(self._h, _ptr(out), out.size, wh))
+        return out
 
     def build_pyramid(self, variant=HIZ_VK):
         self._check(self._lib.blz_cull_build_pyramid(self._h, variant))

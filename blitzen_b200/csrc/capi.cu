@@ -56,16 +56,6 @@ PFN_encodeTiled get_encode_tiled()
     return fn;
 }
 
-ViewConsts make_view_consts(const CameraViewData& v)
-{
-    ViewConsts c;
-    for (int col = 0; col < 4; ++col)
-        for (int row = 0; row < 3; ++row) c.m[col * 3 + row] = v.view[col * 4 + row];
-    c.frustumRight = v.frustumRight; c.frustumLeft = v.frustumLeft; c.frustumTop = v.frustumTop; c.frustumBottom = v.frustumBottom;
-    c.proj0 = v.proj0; c.proj5 = v.proj5; c.zNear = v.zNear; c.zFar = v.zFar;
-    c.pyramidWidth = v.pyramidWidth; c.pyramidHeight = v.pyramidHeight; c.lodTarget = v.lodTarget;
-    return c;
-}
 
 int ensure_status(blz_cull_ctx* c, size_t entries)
 {

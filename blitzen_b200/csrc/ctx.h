@@ -75,6 +75,18 @@ struct blz_cull_ctx {
 
 namespace blz {
 int fail(int code, const char* fmt, ...);
+
+// the part of the 256-byte view block the kernels read, as kernel-parameter constants
+inline ViewConsts make_view_consts(const CameraViewData& v)
+{
+    ViewConsts c;
+    for (int col = 0; col < 4; ++col)
+        for (int row = 0; row < 3; ++row) c.m[col * 3 + row] = v.view[col * 4 + row];
+    c.frustumRight = v.frustumRight; c.frustumLeft = v.frustumLeft; c.frustumTop = v.frustumTop; c.frustumBottom = v.frustumBottom;
+    c.proj0 = v.proj0; c.proj5 = v.proj5; c.zNear = v.zNear; c.zFar = v.zFar;
+    c.pyramidWidth = v.pyramidWidth; c.pyramidHeight = v.pyramidHeight; c.lodTarget = v.lodTarget;
+    return c;
+}
 }
 
 #define CU_TRY(expr)                                                                                          \

@@ -223,6 +223,16 @@ int blz_cull_instances_counts(blz_cull_ctx* ctx, uint32_t* dst_device /* lod_cou
 int blz_cull_instances_push(blz_cull_ctx* ctx, const uint32_t* all_counts_device /* [world][lod_count] */, const uint32_t* global_offset_device, const uint32_t* global_cap_device);
 int blz_cull_gather_outputs(blz_cull_ctx* ctx, void** out_records_device, uint32_t** out_flags_device);
 
+/* ---- device-side software depth ----------------------------------------------------------------------------
+ * Stands in for DrawGeometry filling the depth attachment between the two cull phases (frame order BlitzenVulkan/vulkanDraw.cpp:1015-1036;
+ * attachment cleared to 0, reverse-Z: BlitzenVulkan/vulkanResources.cpp:70-71).  Clears the context's own width x height depth target and
+ * merges (max) into it, for every record of the CURRENT draw list of `list`, the screen-space bounding box of the drawn object's bounding
+ * sphere at the depth of the sphere's far side, zNear / (c.z + r).  The target becomes the depth image blz_cull_build_pyramid reads.
+ * Closed loop of a frame: blz_cull_early -> blz_cull_raster_depth -> blz_cull_build_pyramid -> blz_cull_late. */
+int blz_cull_raster_depth(blz_cull_ctx* ctx, int list, uint32_t width, uint32_t height);
+/* the current depth image (set_depth / set_depth_device / raster_depth); records_host may be NULL to query the extent */
+int blz_cull_read_depth(blz_cull_ctx* ctx, float* depth_host, uint64_t capacity_texels, uint32_t* out_wh /* [2] */);
+
 /* ---- zero-copy hand-over of the outputs --------------------------------------------------------------------
  * Replaces: the renderer reading `indirectDrawBuffer` / `indirectCountBuffer` in vkCmdDrawIndexedIndirectCount
  * (BlitzenVulkan/vulkanDraw.cpp:469-471; buffers created in vulkanRendererSetup.cpp:365-666).  The draw-record buffer and the count

@@ -604,6 +604,43 @@ int oracle_boundary_census(const oracle_scene* sc, const void* view, const oracl
     return 0;
 }
 
+// Software depth (product: blitzen_b200/csrc/raster_depth.cu).  No reference shader does this -- it stands in for the
+// rasteriser between the two cull phases (frame order BlitzenVulkan/vulkanDraw.cpp:1015-1036; clear value 0, reverse-Z:
+// BlitzenVulkan/vulkanResources.cpp:70-71) -- so this is the DEFINITION the CUDA kernel is compared with, built from the reference's own
+// functions: view-space sphere as in IsObjectInsideViewFrustum, screen box from projectSphere, depth of the sphere's far side
+// zNear / (c.z + r), merged with max.  Pixel (x, y) is covered when floor(aabb.x * W) <= x < ceil(aabb.z * W), same in y, clamped.
+static inline uint32_t pix_floor(float f, uint32_t n) { if (!(f >= 0.0f)) return 0u; if (f >= float(n)) return n; return uint32_t(std::floor(f)); }
+static inline uint32_t pix_ceil(float f, uint32_t n) { if (!(f >= 0.0f)) return 0u; if (f >= float(n)) return n; return uint32_t(std::ceil(f)); }
+
+int oracle_raster_depth(const oracle_scene* sc, const void* view, const uint32_t* records, uint64_t nRecords, uint32_t recWords,
+                        uint32_t W, uint32_t H, float* outDepth)
+{
+    Scene S{ (const RenderObject*)sc->objs, sc->nObj, (const MeshTransform*)sc->transforms, (const PrimitiveSurface*)sc->surfaces,
+             (const LodData*)sc->lods, (const Cluster*)sc->clusters, sc->objectIdBase };
+    ViewData V; std::memcpy(&V, view, sizeof(V));
+    for (size_t i = 0; i < size_t(W) * H; ++i) outDepth[i] = 0.0f;
+    for (uint64_t k = 0; k < nRecords; ++k) {
+        const uint32_t local = records[k * recWords] - S.objectIdBase;
+        if (local >= S.nObj) continue;
+        RenderObject obj = S.objs[local];
+        const MeshTransform& T = S.xf[obj.transformId];
+        const PrimitiveSurface& sf = S.surf[obj.surfaceId];
+        vec3 c; float r;
+        IsObjectInsideViewFrustum(c, r, vec3{ sf.center[0], sf.center[1], sf.center[2] }, sf.radius, T.scale,
+            vec3{ T.pos[0], T.pos[1], T.pos[2] }, vec4{ T.q[0], T.q[1], T.q[2], T.q[3] }, V.view,
+            V.frustumRight, V.frustumLeft, V.frustumTop, V.frustumBottom, V.zNear, V.zFar);
+        vec4 aabb;
+        if (!projectSphere(c, r, V.zNear, V.proj0, V.proj5, aabb)) continue;
+        const uint32_t x0 = pix_floor(aabb.x * float(W), W), x1 = pix_ceil(aabb.z * float(W), W);
+        const uint32_t y0 = pix_floor(aabb.y * float(H), H), y1 = pix_ceil(aabb.w * float(H), H);
+        const float d = V.zNear / (c.z + r);
+        if (!(d > 0.0f)) continue;
+        for (uint32_t y = y0; y < y1; ++y)
+            for (uint32_t x = x0; x < x1; ++x) { float& t = outDepth[size_t(y) * W + x]; if (d > t) t = d; }
+    }
+    return 0;
+}
+
 // Per-object debug probe used by the known-answer tests: runs the frustum / projectSphere / Hi-Z / LOD functions for one
 // explicit sphere+transform and returns the intermediate values.
 // out: [0]=visible(frustum) [1..3]=center [4]=radius [5]=projected(0/1) [6..9]=aabb [10]=hiz passed(0/1) [11]=lodIndex(relative)

@@ -9,7 +9,7 @@ SRCS=${@:-cull_stream.cu}
 mkdir -p variants/obj_$NAME
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -Xcompiler -fPIC,-O2,-ffp-contract=off --expt-relaxed-constexpr --extended-lambda -Xptxas -v"
 OBJS=""
-for f in capi.cu cull_stream.cu cull_early.cu cull_cluster.cu cull_list.cu pyramid.cu gather.cu consume.cu interop.cu; do
+for f in capi.cu cull_stream.cu cull_early.cu cull_cluster.cu cull_list.cu pyramid.cu gather.cu consume.cu interop.cu raster_depth.cu; do
   if echo " $SRCS " | grep -q " $f "; then
     nvcc $FLAGS $DEFS -c blitzen_b200/csrc/$f -o variants/obj_$NAME/$f.o > variants/obj_$NAME/$f.log 2>&1 &
     OBJS="$OBJS variants/obj_$NAME/$f.o"

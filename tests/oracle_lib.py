@@ -175,6 +175,16 @@ def boundary_census(objs, transforms, surfaces, lods, view, pyramid, hiz, ulp_to
     return {"near_frustum_plane": int(out[0]), "near_texel_boundary": int(out[1]), "near_mip_boundary": int(out[2]), "near_depth_equal": int(out[3])}
 
 
+def raster_depth(objs, transforms, surfaces, lods, view, records, width, height, object_id_base=0, transform_id_base=0):
+    """Software depth from a draw list (oracle_raster_depth): H x W float32, 0 = far."""
+    s = _scene(objs, transforms, surfaces, lods, None, object_id_base, transform_id_base)
+    v = np.ascontiguousarray(view)
+    rec = np.ascontiguousarray(records).view(np.uint32).reshape(len(records), -1)
+    out = np.zeros((height, width), dtype=np.float32)
+    lib().oracle_raster_depth(C.byref(s), _p(v), _p(rec), C.c_uint64(rec.shape[0]), C.c_uint32(rec.shape[1] if rec.size else 6), C.c_uint32(width), C.c_uint32(height), _p(out))
+    return out
+
+
 def probe(bound_center, bound_radius, transform8, view, pyramid=None, hiz=HIZ_VK, lods=None, lod_offset=0, lod_count=0):
     bc = np.ascontiguousarray(bound_center, dtype=np.float32)
     t8 = np.ascontiguousarray(transform8, dtype=np.float32)
