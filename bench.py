@@ -46,6 +46,12 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-regimes", action="store_true", help="skip the extra device timings of the late kernel's other output regimes")
     ap.add_argument("--hiz", default="vk", choices=["vk", "dx"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs[1] (default, the contract line) or configs[2..4]: instancing 64 M / clusters 256 M records / 8 views x 16.7 M at 4K (bench_configs.py)")
+    ap.add_argument("--depth", default="synthetic", choices=["synthetic", "raster"],
+                    help="synthetic: the seeded 64-rectangle depth image of BASELINE config 2; raster: software depth splatted from the early list every frame (closed loop, csrc/raster_depth.cu)")
+    ap.add_argument("--records", type=int, default=0, help="cfg4: cluster dispatch records in total (default 268 435 456)")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement of the frame")
     return ap.parse_args()
 
 
@@ -184,13 +190,16 @@ def workload_config(args, world):
     return {"workload": "configs[1]: stress-scene mesh mix replicated to 16777216 objects, two-phase frustum + Hi-Z (" + args.hiz.upper() +
                         " variant) + LOD cull, 1920x1080 synthetic depth, view " + VIEW_NAME,
             "objects_per_gpu": args.objects, "objects_total": args.objects * world, "depth": [DEPTH_W, DEPTH_H],
-            "step": "early pass + Hi-Z pyramid build + late pass" + (" + peer-memory draw-list gather (early and late lists, pushed on a side stream behind each pass)" if world > 1 else ""),
+            "step": "early pass + " + ("software depth from the early list + " if getattr(args, "depth", "synthetic") == "raster" else "") + "Hi-Z pyramid build + late pass" + (" + peer-memory draw-list gather (early and late lists, pushed on a side stream behind each pass)" if world > 1 else ""),
             "record_format": "VK24", "l2_policy": "inputs larger than L2 (object + transform streams = 40 B x 16.7 M = 671 MB >> 126 MB)",
             "parallelism": f"object-sharded x{world}"}
 
 
 def main():
     args = parse_args()
+    if args.workload != "cfg2":
+        import bench_configs
+        return bench_configs.run(args)
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -224,8 +233,12 @@ def main():
 
     epoch = [0]
 
+    raster = args.depth == "raster"
+
     def frame():
         ctx.early(capi.REC_VK24)
+        if raster:
+            ctx.raster_depth(DEPTH_W, DEPTH_H)        # reads the early list: before the push flips the draw buffers
         if gather:
             epoch[0] += 1; gather.push_async(epoch[0])
         ctx.build_pyramid(variant)
@@ -260,8 +273,12 @@ def main():
             ev[k][0].record(stream)
             ctx.early(capi.REC_VK24)
             if gather:
+                if raster:
+                    ctx.raster_depth(DEPTH_W, DEPTH_H)
                 epoch[0] += 1; gather.push_async(epoch[0])
             ev[k][1].record(stream)
+            if raster and not gather:
+                ctx.raster_depth(DEPTH_W, DEPTH_H)      # timed with the pyramid: "depth + pyramid"
             ctx.build_pyramid(variant)
             ev[k][2].record(stream)
             ctx.late(capi.REC_VK24, variant)
@@ -285,11 +302,42 @@ def main():
     ms_per_step = total_ms / K
     value = (n * world) / (ms_per_step * 1e-3)
 
+    # ---- one more frame, untimed: counts, the early list's device-side checksum and -- at N > 1 -- the proof that the list GATHERED on the
+    #      presenter is the concatenation of the ranks' lists: the presenter reduces the gathered buffer on the device (csrc/consume.cu) and the
+    #      result must equal the all-reduced sum (xor for id_xor) of the ranks' own reductions, with no pair of records out of ascending order
+    gather_ok = None
+    gsum = []
+
+    def gathered_check(tag):
+        if not gather:
+            return
+        mine = ctx.consume_draws(kind=1)
+        epoch[0] += 1
+        gather.push(epoch[0])
+        t = torch.tensor([int(mine.records), int(mine.index_sum), int(mine.id_sum)], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        x = torch.tensor([int(mine.id_xor) & 0x7FFFFFFFFFFFFFFF, int(mine.id_xor) >> 63], device="cuda", dtype=torch.int64)
+        xs = [torch.zeros_like(x) for _ in range(world)]
+        dist.all_gather(xs, x)
+        if rank == 0:
+            g = ctx.consume_gathered(epoch[0])
+            xo = 0
+            for v in xs:
+                xo ^= int(v[0].item()) | (int(v[1].item()) << 63)
+            same = (int(g.records), int(g.index_sum), int(g.id_sum)) == tuple(int(v) for v in t.tolist()) and int(g.id_xor) == xo and int(g.unsorted) == 0
+            gsum.append({"list": tag, "records": int(g.records), "index_sum": int(g.index_sum), "id_xor": "%016x" % int(g.id_xor), "unsorted": int(g.unsorted), "equals_sum_of_ranks": bool(same)})
+
     early_written, early_total = 0, 0
     ctx.early(capi.REC_VK24); early_written, early_total = ctx.read_count()
     cs = ctx.consume_draws()          # what the indirect draw + vertex stage would read from this list, reduced on the device (csrc/consume.cu)
     early_checksum = {"records": int(cs.records), "index_sum": int(cs.index_sum), "id_xor": "%016x" % int(cs.id_xor), "bad_object": int(cs.bad_object), "bad_lod": int(cs.bad_lod), "unsorted": int(cs.unsorted)}
+    if raster:
+        ctx.raster_depth(DEPTH_W, DEPTH_H)
+    gathered_check("early")
     ctx.build_pyramid(variant); ctx.late(capi.REC_VK24, variant); late_written, late_total = ctx.read_count()
+    gathered_check("late")
+    if gather and rank == 0:
+        gather_ok = all(x["equals_sum_of_ranks"] for x in gsum)
     o = ctx.outputs()
     pyr_texels = sum(max(1, o.pyramid_width >> i) * max(1, o.pyramid_height >> i) for i in range(o.pyramid_mips))
 
@@ -350,6 +398,47 @@ def main():
                 roofline["traffic"] = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
+
+    # ---- the same 3-launch frame replayed from a CUDA graph (SURVEY 8b "CUDA-graph the frame"): device time per frame and the host time it
+    #      takes to enqueue a frame, against plain stream launches.  Measured, not assumed: the frame is three launches. ------------------
+    graph_info = None
+    if world == 1 and not args.no_graph:
+        try:
+            def plain():
+                ctx.early(capi.REC_VK24)
+                if raster:
+                    ctx.raster_depth(DEPTH_W, DEPTH_H)
+                ctx.build_pyramid(variant); ctx.late(capi.REC_VK24, variant)
+            for _ in range(3):
+                plain()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                plain()
+            torch.cuda.synchronize()
+            R = 50
+
+            def measure(fn):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                with torch.cuda.stream(stream):
+                    e0.record(stream)
+                    t0 = time.perf_counter()
+                    for _ in range(R):
+                        fn()
+                    host = time.perf_counter() - t0
+                    e1.record(stream)
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / R, host / R * 1e6
+            for _ in range(5):
+                g.replay()
+            s_ms, s_us = measure(plain)
+            g_ms, g_us = measure(g.replay)
+            graph_info = {"stream_launches": {"device_ms_per_frame": s_ms, "host_enqueue_us_per_frame": s_us},
+                          "graph_replay": {"device_ms_per_frame": g_ms, "host_enqueue_us_per_frame": g_us}, "frames": R}
+        except Exception as ex:          # a capture-illegal call inside the library would surface here
+            graph_info = {"error": str(ex)[:300]}
+            torch.cuda.synchronize()
 
     # ---- end to end through the C ABI with HOST buffers: scene upload + depth upload + frame + draw-list read-back --------
     e2e = None
@@ -453,10 +542,10 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_frame": e2e_frame, "gpu_launches": int(launches),
+                "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_frame": e2e_frame, "gpu_launches": int(launches), "gather_ok": gather_ok,
                 "clocks": clocks,
                 "detail": {"visible_prev_frame": vis_prev, "early_draws": early_total, "late_draws": late_total, "early_list_checksum": early_checksum,
-                           "kernel_ms": {"early": t_early, "pyramid": t_pyr, "late": t_late}, "late_kernel_regimes": regimes, "boundary_census": census}}
+                           "kernel_ms": {"early": t_early, "pyramid": t_pyr, "late": t_late}, "late_kernel_regimes": regimes, "boundary_census": census, "gathered_lists": gsum or None, "cuda_graph": graph_info}}
         print(json.dumps(line), flush=True)
     ctx.close()
     if dist is not None:

@@ -75,7 +75,7 @@ ABI_SYMBOLS = [
     "blz_cull_set_cluster_dispatch", "blz_cull_get_outputs", "blz_cull_read_draws", "blz_cull_read_count",
     "blz_cull_read_visibility", "blz_cull_read_cluster_dispatch", "blz_cull_read_instances", "blz_cull_read_pyramid",
     "blz_cull_gather_export", "blz_cull_gather_import", "blz_cull_gather_configure", "blz_cull_gather_push", "blz_cull_gather_push_async", "blz_cull_gather_join",
-    "blz_cull_gather_read", "blz_cull_gather_outputs", "blz_cull_instances_export", "blz_cull_instances_import", "blz_cull_instances_push", "blz_cull_instances_counts", "blz_cull_consume_draws", "blz_cull_consume_instances", "blz_cull_launch_count", "blz_cull_set_option",
+    "blz_cull_gather_read", "blz_cull_gather_outputs", "blz_cull_instances_export", "blz_cull_instances_import", "blz_cull_instances_push", "blz_cull_instances_counts", "blz_cull_consume_draws", "blz_cull_consume_instances", "blz_cull_consume_gathered", "blz_cull_launch_count", "blz_cull_set_option",
     "blz_cull_export_outputs", "blz_cull_export_fence", "blz_cull_signal_fence", "blz_cull_import_semaphore", "blz_cull_signal_semaphore",
     "blz_cull_raster_depth", "blz_cull_read_depth",
     "blz_interop_import", "blz_interop_release", "blz_interop_wait_fence", "blz_interop_read",
@@ -113,7 +113,7 @@ def load_library():
         "blz_cull_gather_configure": [vp, u64, i], "blz_cull_gather_push": [vp, u32], "blz_cull_gather_push_async": [vp, u32], "blz_cull_gather_join": [vp],
         "blz_cull_gather_read": [vp, u32, vp, u64, vp], "blz_cull_gather_outputs": [vp, C.POINTER(vp), C.POINTER(vp)],
         "blz_cull_instances_export": [vp, vp], "blz_cull_instances_import": [vp, vp, i, i], "blz_cull_instances_push": [vp, vp, vp, vp], "blz_cull_instances_counts": [vp, vp],
-        "blz_cull_consume_draws": [vp, i, i, vp], "blz_cull_consume_instances": [vp, i, vp],
+        "blz_cull_consume_draws": [vp, i, i, vp], "blz_cull_consume_instances": [vp, i, vp], "blz_cull_consume_gathered": [vp, u32, vp],
         "blz_cull_launch_count": [vp, C.POINTER(u64)], "blz_cull_set_option": [vp, C.c_char_p, C.c_int64],
         "blz_cull_export_outputs": [vp, C.POINTER(ExportedOutputs)], "blz_cull_export_fence": [vp, vp], "blz_cull_signal_fence": [vp],
         "blz_cull_import_semaphore": [vp, i, i], "blz_cull_signal_semaphore": [vp, u64],
@@ -398,6 +398,11 @@ class CullContext:
     def consume_draws(self, list_id=LIST_OPAQUE, kind=0):
         out = ConsumeSummary()
         self._check(self._lib.blz_cull_consume_draws(self._h, list_id, kind, C.byref(out)))
+        return out
+
+    def consume_gathered(self, epoch):
+        out = ConsumeSummary()
+        self._check(self._lib.blz_cull_consume_gathered(self._h, int(epoch), C.byref(out)))
         return out
 
     def consume_instances(self, list_id=LIST_OPAQUE):

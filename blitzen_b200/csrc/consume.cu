@@ -149,6 +149,39 @@ int blz_cull_consume_draws(blz_cull_ctx* c, int list, int kind, blz_consume_summ
     return BLZ_OK;
 }
 
+// The same reduction over the list the ranks GATHERED on this (the presenting) context for `epoch` (gather.cu): the presenter does not hold the
+// other ranks' objects, so only the record-level part of the summary is produced (kind 1: no object / LOD look-ups).  Equality of this summary
+// with the sum (xor for id_xor) of the ranks' own blz_cull_consume_draws(kind 1) summaries proves the gather on the device, at full size.
+int blz_cull_consume_gathered(blz_cull_ctx* c, uint32_t epoch, blz_consume_summary* out)
+{
+    if (!c || !out) return fail(BLZ_ERR_INVALID, "null argument");
+    if (!c->gatherOwner || !c->gatherBuf) return fail(BLZ_ERR_STATE, "only the presenting rank (the exporter) holds a gathered list");
+    CU_TRY(cudaSetDevice(c->device));
+    uint32_t counts[64];
+    int rc = blz_cull_gather_read(c, epoch, nullptr, 0, counts);            // waits (on the device) for every rank's push of that epoch
+    if (rc) return rc;
+    uint64_t total = 0;
+    for (int r = 0; r < c->world; ++r) total += counts[r];
+    if (total > c->gatherCap) total = c->gatherCap;
+    const uint32_t total32 = uint32_t(total);
+    DeviceSummary* d = nullptr;
+    CU_TRY(cudaMalloc(&d, sizeof(DeviceSummary) + 16));
+    CU_TRY(cudaMemsetAsync(d, 0, sizeof(DeviceSummary), c->stream));
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(d + 1);
+    CU_TRY(cudaMemcpyAsync(cnt, &total32, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    ConsumeParams p{};
+    p.draws = c->gatherBuf + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords; p.counts = cnt; p.recWords = c->gatherRecWords;
+    p.objs = nullptr; p.n = 0xFFFFFFFFu; p.objectIdBase = 0u; p.kind = 1; p.out = d;
+    consume_draws_kernel<<<c->numSMs * 4, kConsumeThreads, 0, c->stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, sizeof(DeviceSummary), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    c->launches++;
+    if (e != cudaSuccess) return fail(BLZ_ERR_CUDA, "consume_gathered: %s", cudaGetErrorString(e));
+    return BLZ_OK;
+}
+
 int blz_cull_consume_instances(blz_cull_ctx* c, int list, blz_consume_summary* out)
 {
     if (!c || !out) return fail(BLZ_ERR_INVALID, "null argument");

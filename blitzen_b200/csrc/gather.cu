@@ -127,6 +127,15 @@ __global__ void __launch_bounds__(kGatherThreads) gather_instances_kernel(const 
     const uint32_t* s = p.src + p.local[l].instanceOffset;
     uint32_t* d = p.dst + size_t(p.globalOffset[l]) + base;
     for (uint32_t i = blockIdx.x * kGatherThreads + threadIdx.x; i < cnt; i += gridDim.x * kGatherThreads) d[i] = s[i];
+    __threadfence_system();      // the peer stores are visible system-wide before the kernel ends: the completion collective that follows on this stream covers them
+}
+
+// what a rank's bucket of LOD l really holds: min(instanceCount, local bucket capacity) -- the words the ranks all-gather, so that the
+// exclusive scan over the lower ranks (the bucket's base on the presenter) counts exactly the ids that will be stored there: no holes
+__global__ void instance_counts_kernel(const LodInstanceCounter* li, const uint32_t* cap, uint32_t lodCount, uint32_t* dst)
+{
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < lodCount) { const uint32_t c = li[l].instanceCount; dst[l] = c < cap[l] ? c : cap[l]; }
 }
 
 } // namespace
@@ -343,13 +352,16 @@ int blz_cull_instances_push(blz_cull_ctx* c, const uint32_t* allCounts, const ui
     return BLZ_OK;
 }
 
-// the per-LOD instanceCount words of the last instancing pass, packed into a caller-owned DEVICE array (stream-ordered): what the host layer all-gathers
+// the per-LOD number of ids the last instancing pass STORED (instanceCount clamped to the bucket capacity), packed into a caller-owned DEVICE array
+// (stream-ordered): what the host layer all-gathers
 int blz_cull_instances_counts(blz_cull_ctx* c, uint32_t* dstDevice)
 {
     if (!c || !c->lodInst || !dstDevice) return fail(BLZ_ERR_INVALID, "scene was uploaded without lod_instances");
     CU_TRY(cudaSetDevice(c->device));
-    CU_TRY(cudaMemcpy2DAsync(dstDevice, sizeof(uint32_t), reinterpret_cast<const unsigned char*>(c->lodInst) + offsetof(LodInstanceCounter, instanceCount),
-                             sizeof(LodInstanceCounter), sizeof(uint32_t), c->nLods, cudaMemcpyDeviceToDevice, c->stream));
+    if (!c->bucketCap) return fail(BLZ_ERR_INVALID, "scene was uploaded without bucket capacities");
+    instance_counts_kernel<<<(c->nLods + 127u) / 128u, 128, 0, c->stream>>>(c->lodInst, c->bucketCap, c->nLods, dstDevice);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
     return BLZ_OK;
 }
 

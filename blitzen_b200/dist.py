@@ -74,19 +74,26 @@ class InstanceListGather:
         ctx.instances_import(None if rank == 0 else t.cpu().numpy(), rank, world)
         self.mine = torch.zeros(n_lods, dtype=torch.int32, device="cuda")
         self.all = torch.zeros(world * n_lods, dtype=torch.int32, device="cuda")
+        self.done = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.goff = torch.from_numpy(np.ascontiguousarray(global_offset, dtype=np.uint32).view(np.int32)).cuda()
         self.gcap = torch.from_numpy(np.ascontiguousarray(global_cap, dtype=np.uint32).view(np.int32)).cuda()
         dist.barrier()
 
     def push(self):
-        """After ctx.instanced() on every rank; stream-ordered, no host synchronisation."""
+        """After ctx.instanced() on every rank; stream-ordered, no host synchronisation.  Ordering protocol (both ends are collectives on the
+        context's stream): the all-gather of the counts cannot complete before the PRESENTER has reached this push on its own stream, i.e.
+        behind whatever it enqueued to consume the previous frame's buckets -- no rank overwrites buckets that are still being read; the
+        one-word all-reduce at the end completes on the presenter only after every rank's peer stores have been issued and fenced
+        (__threadfence_system at the end of the push kernel) -- work enqueued behind push() on the presenter sees complete buckets.  Both
+        collectives are inside what the benchmarks time."""
         import torch
         import torch.distributed as dist
         with torch.cuda.stream(self.stream):
             self.ctx.instances_counts(self.mine.data_ptr())
             dist.all_gather_into_tensor(self.all, self.mine)
             self.ctx.instances_push(self.all.data_ptr(), self.goff.data_ptr(), self.gcap.data_ptr())
+            dist.all_reduce(self.done)
 
     def totals(self):
-        """Per-LOD totals over all ranks (host; synchronises)."""
+        """Per-LOD number of ids stored over all ranks (each rank's count clamped to its bucket capacity; host; synchronises)."""
         return self.all.view(self.world, self.n_lods).sum(dim=0).cpu().numpy().astype(np.uint32)

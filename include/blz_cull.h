@@ -191,6 +191,9 @@ typedef struct blz_consume_summary {
 } blz_consume_summary;
 int blz_cull_consume_draws(blz_cull_ctx* ctx, int list, int kind, blz_consume_summary* out_host);
 int blz_cull_consume_instances(blz_cull_ctx* ctx, int list, blz_consume_summary* out_host);
+/* presenting rank only: the record-level summary (kind 1) of the list gathered for `epoch`; equals the sum (xor for id_xor) of the ranks' own
+ * blz_cull_consume_draws(kind 1) summaries when the gather is correct -- a device-side proof at full size (bench.py prints it as gather_ok) */
+int blz_cull_consume_gathered(blz_cull_ctx* ctx, uint32_t epoch, blz_consume_summary* out_host);
 
 /* ---- multi-GPU draw-list gather (new; the reference is single-GPU) -------------------------------------------------
  * Each rank culls its shard; the per-rank lists are concatenated in shard order on the presenting rank.
