@@ -235,13 +235,16 @@ def main():
 
     raster = args.depth == "raster"
 
+    # The early list is pushed BEHIND the pyramid launch (the pyramid does not touch the draw buffer): next to each other the push's bulk
+    # stores and the pyramid's TMA tile loads queue on the same per-SM copy engine and the 15 us pyramid build took 31 us on the
+    # pushing ranks (trace: scripts/trace_frames.py, profiles/r02e_trace_n2.txt); next to the 175 us late pass the push costs nothing.
     def frame():
         ctx.early(capi.REC_VK24)
         if raster:
             ctx.raster_depth(DEPTH_W, DEPTH_H)        # reads the early list: before the push flips the draw buffers
+        ctx.build_pyramid(variant)
         if gather:
             epoch[0] += 1; gather.push_async(epoch[0])
-        ctx.build_pyramid(variant)
         ctx.late(capi.REC_VK24, variant)
         if gather:
             epoch[0] += 1; gather.push_async(epoch[0])
@@ -268,19 +271,23 @@ def main():
     sampler.start()
     with torch.cuda.stream(stream):
         t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+        if dist is not None:
+            # the host-side barrier above leaves the ranks' STREAMS up to a millisecond apart (host wake-up skew), which a 20-step run would
+            # charge to the gather (a rank's push waits for the lower ranks' counts): one collective ON the launching stream lines the
+            # devices up to within microseconds right before the first timed event.  The timed region is still exactly K steps.
+            align = torch.zeros(1, device="cuda")
+            dist.all_reduce(align)
         t_start.record(stream)
         for k in range(K):
             ev[k][0].record(stream)
             ctx.early(capi.REC_VK24)
-            if gather:
-                if raster:
-                    ctx.raster_depth(DEPTH_W, DEPTH_H)
-                epoch[0] += 1; gather.push_async(epoch[0])
             ev[k][1].record(stream)
-            if raster and not gather:
+            if raster:
                 ctx.raster_depth(DEPTH_W, DEPTH_H)      # timed with the pyramid: "depth + pyramid"
             ctx.build_pyramid(variant)
             ev[k][2].record(stream)
+            if gather:
+                epoch[0] += 1; gather.push_async(epoch[0])
             ctx.late(capi.REC_VK24, variant)
             ev[k][3].record(stream)
             if gather:

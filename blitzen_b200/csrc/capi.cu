@@ -750,6 +750,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     }
     if (strcmp(name, "early_auto") == 0) { c->optEarlyAuto = value; c->earlyDense = false; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
+    if (strcmp(name, "gather_tma") == 0) { c->optGatherTma = value; return BLZ_OK; }
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);
 }
 
