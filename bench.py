@@ -234,16 +234,21 @@ def main():
     epoch = [0]
 
     raster = args.depth == "raster"
+    # where the early list's push starts: behind the pyramid launch up to 4 ranks (the push then overlaps only the 175 us late pass and the
+    # 15 us pyramid build keeps the SMs' copy/store paths to itself), right behind the early pass beyond (the presenter ingests >= 75 MB per
+    # frame and needs more of the frame for it).  Measured, ms per frame (profiles/r02h_n8_ab.txt): N=2 0.2437 / 0.2573, N=4 0.2465 / 0.2668,
+    # N=8 0.3601 / 0.2933 (pyramid / early).  BLZ_PUSH_AFTER overrides.
+    push_early_first = os.environ.get("BLZ_PUSH_AFTER", "early" if world > 4 else "pyramid") == "early"
 
-    # The early list is pushed BEHIND the pyramid launch (the pyramid does not touch the draw buffer): next to each other the push's bulk
-    # stores and the pyramid's TMA tile loads queue on the same per-SM copy engine and the 15 us pyramid build took 31 us on the
-    # pushing ranks (trace: scripts/trace_frames.py, profiles/r02e_trace_n2.txt); next to the 175 us late pass the push costs nothing.
+    # The early list is pushed by a throttled number of small co-resident CTAs (csrc/gather.cu) on a side stream; see push_early_first.
     def frame():
         ctx.early(capi.REC_VK24)
         if raster:
             ctx.raster_depth(DEPTH_W, DEPTH_H)        # reads the early list: before the push flips the draw buffers
+        if gather and push_early_first:
+            epoch[0] += 1; gather.push_async(epoch[0])
         ctx.build_pyramid(variant)
-        if gather:
+        if gather and not push_early_first:
             epoch[0] += 1; gather.push_async(epoch[0])
         ctx.late(capi.REC_VK24, variant)
         if gather:
@@ -264,6 +269,7 @@ def main():
 
     # ---- timed region: exactly K frames, CUDA events on the launching stream, per-kernel events inside -------------------
     K = args.steps
+    EV_EVERY = 4
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launch_count()
@@ -279,17 +285,22 @@ def main():
             dist.all_reduce(align)
         t_start.record(stream)
         for k in range(K):
-            ev[k][0].record(stream)
+            # per-kernel events on every 4th step only: an event record costs the stream ~3 us (measured: 4 per step made the step
+            # 0.2486 ms, none 0.2357 ms), which is launch overhead of the harness, not of the path
+            timed_k = (k % EV_EVERY) == 0
+            if timed_k: ev[k][0].record(stream)
             ctx.early(capi.REC_VK24)
-            ev[k][1].record(stream)
+            if timed_k: ev[k][1].record(stream)
             if raster:
                 ctx.raster_depth(DEPTH_W, DEPTH_H)      # timed with the pyramid: "depth + pyramid"
+            if gather and push_early_first:
+                epoch[0] += 1; gather.push_async(epoch[0])
             ctx.build_pyramid(variant)
-            ev[k][2].record(stream)
-            if gather:
+            if timed_k: ev[k][2].record(stream)
+            if gather and not push_early_first:
                 epoch[0] += 1; gather.push_async(epoch[0])
             ctx.late(capi.REC_VK24, variant)
-            ev[k][3].record(stream)
+            if timed_k: ev[k][3].record(stream)
             if gather:
                 epoch[0] += 1; gather.push_async(epoch[0])
         if gather:
@@ -299,9 +310,10 @@ def main():
     clocks = sampler.stop()
     launches = ctx.launch_count() - launches0
     total_ms = t_start.elapsed_time(t_end)
-    t_early = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]))
-    t_pyr = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]))
-    t_late = float(np.mean([ev[k][2].elapsed_time(ev[k][3]) for k in range(K)]))
+    ks = range(0, K, EV_EVERY)
+    t_early = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in ks]))
+    t_pyr = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in ks]))
+    t_late = float(np.mean([ev[k][2].elapsed_time(ev[k][3]) for k in ks]))
     if dist is not None:
         tt = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -393,7 +405,7 @@ def main():
     late_gbs = b_late / (t_late * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "stream_cull_kernel<PASS_LATE> (late pass: frustum + Hi-Z + LOD + compaction + visibility write)",
                 "achieved": late_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": late_gbs / peak,
-                "algorithmic_bytes_per_launch": b_late, "bytes_per_object": 48, "objects_per_launch": n, "launch_ms": t_late,
+                "algorithmic_bytes_per_launch": b_late, "bytes_per_object": 48, "objects_per_launch": n, "launch_ms": t_late, "launch_ms_sampled_steps": len(list(ks)),
                 "traffic": None,
                 "other_kernels": {"early": {"ms": t_early, "algorithmic_bytes": b_early, "GBps": b_early / (t_early * 1e-3) / 1e9},
                                   "pyramid": {"ms": t_pyr, "algorithmic_bytes": b_pyr, "GBps": b_pyr / (t_pyr * 1e-3) / 1e9}},

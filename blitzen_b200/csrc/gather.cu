@@ -363,12 +363,19 @@ int blz_cull_gather_push_async(blz_cull_ctx* c, uint32_t epoch)
     if (!c->drawsAlt) CU_TRY(cudaMalloc(&c->drawsAlt, c->capDraws));
     CU_TRY(cudaEventRecord(c->evCull, c->stream));
     CU_TRY(cudaStreamWaitEvent(c->gatherStream, c->evCull, 0));
-    // few CTAs: the presenter's NVLink ingest (900 GB/s) is shared by world - 1 pushers, and every resident push CTA takes a slot away
-    // from the pass running next to it on the main stream
+    // How many co-resident 64-thread CTAs push: the presenter's kernels slow down while it ingests (world - 1) lists at once, so the ranks
+    // throttle themselves -- the list has the rest of the frame to arrive.  Measured at 8 GPUs (profiles/r02h_n8_ab.txt, ms per frame):
+    // 148 CTAs 0.308 (pyramid next to the push 0.053 ms), 16 CTAs 0.290, 4 CTAs 0.746 (the push itself becomes the frame).
     static const int envCtas = [] { const char* e = getenv("BLZ_GATHER_CTAS"); return e ? atoi(e) : 0; }();
-    int ctas = envCtas > 0 ? envCtas : 56 / (c->world > 1 ? c->world - 1 : 1);        // measured at 8 GPUs: 8 CTAs 0.317 ms/frame, 16: 0.329, 32: 0.346
-    ctas = ctas < 4 ? 4 : (ctas > 32 ? 32 : ctas);
-    if (c->optGatherTma != 0) ctas = envCtas > 0 ? envCtas : c->numSMs;              // co-resident with the cull kernels: one CTA per SM
+    int ctas;
+    if (c->optGatherTma != 0) {
+        ctas = 224 / (c->world > 1 ? c->world - 1 : 1);
+        ctas = ctas < 16 ? 16 : (ctas > 64 ? 64 : ctas);
+    } else {
+        ctas = 56 / (c->world > 1 ? c->world - 1 : 1);                               // r01 kernel (256-thread CTAs): 8 CTAs at 8 GPUs
+        ctas = ctas < 4 ? 4 : (ctas > 32 ? 32 : ctas);
+    }
+    if (envCtas > 0) ctas = envCtas;
     rc = gather_launch(c, epoch, c->gatherStream, ctas); if (rc) return rc;
     CU_TRY(cudaEventRecord(c->evPush[c->drawSlot], c->gatherStream));
     c->evPushValid[c->drawSlot] = true;
