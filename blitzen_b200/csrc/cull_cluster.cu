@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kCullThreads, MINB) cluster_cull_kernel(const 
     if (M > p.maxRecords) M = p.maxRecords;
     const uint32_t numTiles = M == 0u ? 1u : (M + uint32_t(TILE) - 1u) / uint32_t(TILE);
     const ViewConsts& V = p.view;
-    const bool sphereMode = p.mode != 0u;
+    constexpr bool sphereMode = true;        // the passthrough mode has its own kernel below; as a run-time flag in this one it cost registers (cf. cull_stream.cu, r02)
     const uint32_t cap32 = p.capacity > 0xFFFFFFFFull ? 0xFFFFFFFFu : uint32_t(p.capacity);
     const uint32_t localBase = warp * uint32_t(WSPAN) + lane;
     const uint64_t polStream = l2_policy_evict_first(), polTable = l2_policy_evict_last();
@@ -455,7 +455,7 @@ cudaError_t launch_cluster_cull(const ClusterCullParams& p, int hiz, int numSMs,
     static const int envCfg = [] { const char* e = getenv("BLZ_CLUSTER_CFG"); return e ? atoi(e) : -1; }();   // tuning aid (scripts/inst_cluster_microbench.py)
     // defaults from the s2x sweeps (profiles/r01l_cluster_sweep.txt): 4 records per thread x 2 CTAs/SM without Hi-Z (no spills, the
     // prefetch hides the gathers), 3 x 3 with Hi-Z (the projection / Hi-Z arithmetic wants resident warps)
-    if (p.mode == 0u && envCfg < 0) return launch_cluster_passthrough(p, numSMs, stream);
+    if (p.mode == 0u) return launch_cluster_passthrough(p, numSMs, stream);
     if (p.mode != 2u) return launch_cluster_hiz<HIZ_NONE>(p, envCfg >= 0 ? envCfg : 0, numSMs, stream);
     const int cfg = envCfg >= 0 ? envCfg : 4;
     return hiz == HIZ_VK ? launch_cluster_hiz<HIZ_VK>(p, cfg, numSMs, stream) : launch_cluster_hiz<HIZ_DX>(p, cfg, numSMs, stream);

@@ -120,13 +120,20 @@ __device__ __forceinline__ int ilog2_floor_pos(float x)
 __device__ __forceinline__ uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 __device__ __forceinline__ float min_keep(float a, float b) { return b < a ? b : a; }
 
-// clamp a float texel index to [0, n-1]; NaN -> 0
+// clamp a float texel index to [0, n-1]; NaN -> 0.  Written as  !(f >= 0) ? 0 : f >= float(n-1) ? n-1 : uint(f)  in the oracle; the
+// saturating float -> int conversion (F2I.RZ: NaN -> 0, out of range -> INT_MIN / INT_MAX) followed by an integer clamp gives the same
+// value for EVERY float (n - 1 < 2^31): three instructions instead of nine, four times per Hi-Z sample
 __device__ __forceinline__ uint32_t clamp_index(float f, uint32_t n)
 {
+#ifdef BLZ_CLAMP_INDEX_COMPARE
     if (!(f >= 0.0f)) return 0u;
     float hi = float(n - 1);
     if (f >= hi) return n - 1;
     return uint32_t(f);
+#else
+    const int t = __float2int_rz(f);
+    return uint32_t(min(max(t, 0), int(n - 1u)));
+#endif
 }
 
 // LINEAR + VK_SAMPLER_REDUCTION_MODE_MIN + CLAMP_TO_EDGE sample of one mip (BlitzenVulkan/vulkanResources.cpp:51-55, :394-429):
