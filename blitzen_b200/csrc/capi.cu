@@ -68,6 +68,21 @@ int ensure_status(blz_cull_ctx* c, size_t entries)
     return BLZ_OK;
 }
 
+// Tile status words are never cleared: a word is valid only if it carries the current launch's 30-bit tag (ScanCtl::epoch, bumped by the last
+// CTA out of every scan kernel).  The tag would wrap after 2^30 launches (about a day at several thousand launches per second) and a slot that
+// smaller passes did not rewrite in the meantime would then be accepted with a stale value.  The host counts the same launches and,
+// well before the wrap, clears the status array and restarts the tag -- stream-ordered, two tiny operations once per ~10^9 launches.
+int scan_epoch_guard(blz_cull_ctx* c)
+{
+    if (++c->epochLaunches < c->epochWrapAt) return BLZ_OK;
+    static const ScanCtl restart{ 0u, 0u, 1u, 0u };
+    if (c->status && c->statusEntries) CU_TRY(cudaMemsetAsync(c->status, 0, c->statusEntries * sizeof(uint64_t), c->stream));
+    CU_TRY(cudaMemcpyAsync(c->ctl, &restart, sizeof(restart), cudaMemcpyHostToDevice, c->stream));
+    c->epochLaunches = 1;
+    c->epochRestarts++;
+    return BLZ_OK;
+}
+
 uint32_t tiles_for(uint64_t n) { return n == 0 ? 1u : uint32_t((n + kCullTile - 1) / kCullTile); }
 
 void pyramid_layout(uint32_t depthW, uint32_t depthH, int variant, PyramidDesc& d, size_t& texels)
@@ -199,6 +214,7 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     if (usesBits) { TRY_RC(ensure_vis_bits(c)); p.visBits = c->visBits; }
     if (usesWords) TRY_RC(ensure_vis_words(c));
     if (pass == PASS_LATE && !c->optVisWords) p.visibility = nullptr;    // the mask is the state; the u32 form is materialised on demand
+    TRY_RC(scan_epoch_guard(c));
     if (earlyStream) CU_TRY(launch_early_stream(p, c->numSMs, c->stream));
     else CU_TRY(launch_stream_cull(p, pass, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, int(c->optStreamCfg), c->numSMs, c->stream));
     if (earlyAuto && !earlyStream) {       // dense frame: the streaming kernel does not count; a 2 MB popcount + a 4-byte copy next to a 0.18 ms pass
@@ -238,6 +254,7 @@ int run_survivor_list(blz_cull_ctx* c, int list)
     p.capacity = n;
     p.view = make_view_consts(c->view);
     p.pyr = c->pyr;
+    TRY_RC(scan_epoch_guard(c));
     CU_TRY(launch_stream_cull(p, PASS_FRUSTUM, HIZ_VK, int(c->optStreamCfg), c->numSMs, c->stream));
     c->launches++;
     return BLZ_OK;
@@ -611,6 +628,7 @@ int blz_cull_cluster_cull(blz_cull_ctx* c, int mode, int fmt, int hiz)
     p.objectIdBase = c->objectIdBase; p.transformIdBase = c->transformIdBase; p.clusterCount = c->nClusters;
     p.recWords = fmt == BLZ_REC_VK24 ? 6u : 8u; p.mode = uint32_t(mode); p.capacity = c->drawCap;
     p.view = make_view_consts(c->view); p.pyr = c->pyr;
+    TRY_RC(scan_epoch_guard(c));
     CU_TRY(launch_cluster_cull(p, hiz == BLZ_HIZ_DX ? HIZ_DX : HIZ_VK, c->numSMs, c->stream));
     c->launches++;
     c->lastRecWords = p.recWords;
@@ -751,6 +769,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (strcmp(name, "early_auto") == 0) { c->optEarlyAuto = value; c->earlyDense = false; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     if (strcmp(name, "gather_tma") == 0) { c->optGatherTma = value; return BLZ_OK; }
+    if (strcmp(name, "epoch_wrap_at") == 0) { if (value < 4) return fail(BLZ_ERR_INVALID, "epoch_wrap_at < 4"); c->epochWrapAt = uint32_t(value); return BLZ_OK; }   // tests: restart the status tag every `value` launches
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);
 }
 

@@ -53,6 +53,7 @@ struct blz_cull_ctx {
     // view
     blz::CameraViewData view{}; bool haveView = false;
     uint64_t launches = 0;
+    uint32_t epochLaunches = 1, epochWrapAt = (1u << 30) - 1024u, epochRestarts = 0;   // host mirror of ScanCtl::epoch (scan_epoch_guard in capi.cu)
     int64_t optPyramidTma = 1;
     int64_t optEarlyMode = 1;                 // 1 = pipelined visibility-stream kernel (cull_early.cu), 0 = the streaming kernel (cull_stream.cu, PASS_EARLY) whatever the density
     int64_t optEarlyBits = 1;                 // pipelined early pass streams the 1-bit mask (1) or the 4-B visibility words (0)

@@ -501,3 +501,24 @@ def test_pyramid_4k_and_late(capi, medium_scene, variant):
             assert gtot == l_tot and np.array_equal(recs_u32(got), l_exp)
             assert np.array_equal(ctx.read_visibility(), vis_exp)
     assert 0 < int(vis_exp.sum()) < n
+
+
+def test_status_tag_restart(capi, medium_scene):
+    """the 30-bit tag of the tile status words must not wrap into stale slots.  Option epoch_wrap_at makes the host-side
+    guard restart the tag (clear the status array, epoch = 1) every few launches; passes of different tile counts stay byte-exact."""
+    sc = medium_scene
+    view = view_at(position=(950, 950, 950), z_far=5000.0)
+    exp, total, _ = O.cull(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM, threads=8)
+    small = 70_001
+    exp_s, total_s, _ = O.cull(sc["objs"][:small], sc["transforms"], sc["surfaces"], sc["lods"], view, O.PASS_FRUSTUM, threads=8)
+    with make_ctx(capi, sc) as ctx, make_ctx(capi, dict(sc, objs=sc["objs"][:small])) as ctx_s:
+        for c in (ctx, ctx_s):
+            c.set_view(view)
+            c.set_option("epoch_wrap_at", 5)
+        for it in range(14):                       # several restarts, at different points of the early / late / frustum sequence
+            ctx.frustum_lod()
+            got, gtot = ctx.read_draws()
+            assert gtot == total and np.array_equal(recs_u32(got), exp), it
+            ctx_s.frustum_lod()
+            got, gtot = ctx_s.read_draws()
+            assert gtot == total_s and np.array_equal(recs_u32(got), exp_s), it
