@@ -416,8 +416,11 @@ def main():
             import hashlib
             with open(prof) as f:
                 tr = json.load(f)
-            with open(os.path.join(ROOT, "blitzen_b200", "csrc", "cull_stream.cu"), "rb") as f:
-                same = hashlib.sha256(f.read()).hexdigest() == tr.get("kernel_source_sha256")
+            hh = hashlib.sha256()
+            for fn in tr.get("kernel_source_files", []):
+                with open(os.path.join(ROOT, fn), "rb") as f:
+                    hh.update(f.read())
+            same = hh.hexdigest() == tr.get("kernel_source_sha256")
             roofline["traffic"] = tr.get("dram_bytes_per_launch") if same else None      # an ncu figure of ANOTHER version of the kernel is not reported
             roofline["traffic_source"] = tr.get("source") if same else "stale: the kernel source changed since the ncu capture in profiles/late_traffic.json"
         except Exception:
