@@ -164,6 +164,7 @@ int check_list(blz_cull_ctx* c, int list)
 {
     if (list < 0 || list > 2) return fail(BLZ_ERR_INVALID, "list %d out of range", list);
     if (!c->surf || !c->lods) return fail(BLZ_ERR_INVALID, "no scene uploaded");
+    if (c->sceneRefused) return fail(BLZ_ERR_STATE, "no scene: the last upload was refused by validation");
     if (!c->haveView) return fail(BLZ_ERR_INVALID, "no view set");
     return BLZ_OK;
 }
@@ -267,6 +268,8 @@ extern "C" {
 int blz_cull_abi_version(void) { return BLZ_CULL_ABI_VERSION; }
 const char* blz_cull_last_error(void) { return g_lastError.c_str(); }
 
+static int create_resources(blz_cull_ctx* c);
+
 int blz_cull_create(int device, blz_cull_ctx** out)
 {
     if (!out) return fail(BLZ_ERR_INVALID, "out_ctx is null");
@@ -279,9 +282,18 @@ int blz_cull_create(int device, blz_cull_ctx** out)
     blz_cull_ctx* c = new (std::nothrow) blz_cull_ctx();
     if (!c) return fail(BLZ_ERR_INVALID, "out of host memory");
     c->device = device;
+    const int rc = create_resources(c);
+    if (rc) { const std::string msg = g_lastError; blz_cull_destroy(c); g_lastError = msg; return rc; }   // nothing allocated so far is leaked
+    *out = c;
+    return BLZ_OK;
+}
+
+static int create_resources(blz_cull_ctx* c)
+{
+    const int device = c->device;
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) { delete c; return fail(BLZ_ERR_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor); }
+    if (prop.major < 10) return fail(BLZ_ERR_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
     c->numSMs = prop.multiProcessorCount;
     CU_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
     c->stream = c->ownStream;
@@ -296,7 +308,6 @@ int blz_cull_create(int device, blz_cull_ctx** out)
     CU_TRY(cudaMalloc(&c->pyrTicket, sizeof(uint32_t)));
     CU_TRY(cudaMemsetAsync(c->pyrTicket, 0, sizeof(uint32_t), c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
-    *out = c;
     return BLZ_OK;
 }
 
@@ -350,6 +361,53 @@ int blz_cull_synchronize(blz_cull_ctx* c)
     if (c->gatherStream) CU_TRY(cudaStreamSynchronize(c->gatherStream));
     return BLZ_OK;
 }
+
+namespace {
+
+// Scene validation: the kernels index surfaces / transforms / LODs / clusters with the ids they find in the scene; a malformed
+// scene must come back as BLZ_ERR_INVALID from upload_scene, not as an out-of-bounds access in a later pass.  One pass over what was
+// just uploaded; the four violation counts travel back in one 16-byte copy.
+__global__ void validate_objects_kernel(const RenderObject* objs, uint32_t n, uint32_t nSurf, uint32_t transformIdBase, uint32_t nXf, uint32_t* bad)
+{
+    uint32_t bs = 0u, bt = 0u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const RenderObject o = objs[i];
+        if (o.surfaceId >= nSurf) ++bs;
+        if (o.transformId - transformIdBase >= nXf) ++bt;
+    }
+    bs = __reduce_add_sync(0xFFFFFFFFu, bs); bt = __reduce_add_sync(0xFFFFFFFFu, bt);
+    if ((threadIdx.x & 31u) == 0u) { if (bs) atomicAdd(bad + 0, bs); if (bt) atomicAdd(bad + 1, bt); }
+}
+__global__ void validate_tables_kernel(const PrimitiveSurface* surf, uint32_t nSurf, const LodData* lods, uint32_t nLods, uint32_t nClusters, uint32_t* bad)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nSurf && (surf[i].lodCount == 0u || uint64_t(surf[i].lodOffset) + surf[i].lodCount > nLods)) atomicAdd(bad + 2, 1u);
+    if (i < nLods && nClusters != 0u && uint64_t(lods[i].clusterOffset) + lods[i].clusterCount > nClusters) atomicAdd(bad + 3, 1u);
+}
+
+int validate_scene(blz_cull_ctx* c)
+{
+    uint32_t* bad = c->counts + 12;                                  // four spare words of the count block
+    CU_TRY(cudaMemsetAsync(bad, 0, 4 * sizeof(uint32_t), c->stream));
+    for (int i = 0; i < 3; ++i)
+        if (c->nObjs[i]) {
+            validate_objects_kernel<<<c->numSMs * 8, 256, 0, c->stream>>>(c->objs[i], c->nObjs[i], c->nSurf, c->transformIdBase, c->nXf, bad);
+            c->launches++;
+        }
+    const uint32_t m = c->nSurf > c->nLods ? c->nSurf : c->nLods;
+    validate_tables_kernel<<<(m + 255u) / 256u, 256, 0, c->stream>>>(c->surf, c->nSurf, c->lods, c->nLods, c->nClusters, bad);
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    uint32_t h[4] = { 0, 0, 0, 0 };
+    CU_TRY(cudaMemcpyAsync(h, bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (h[0] | h[1] | h[2] | h[3])
+        return fail(BLZ_ERR_INVALID, "malformed scene: %u objects with surfaceId >= %u, %u with a transformId outside [%u, %u), %u surfaces whose LOD range leaves the %u LODs, "
+                    "%u LODs whose cluster range leaves the %u clusters", h[0], c->nSurf, h[1], c->transformIdBase, c->transformIdBase + c->nXf, h[2], c->nLods, h[3], c->nClusters);
+    return BLZ_OK;
+}
+
+} // namespace
 
 int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
 {
@@ -451,6 +509,11 @@ int blz_cull_upload_scene(blz_cull_ctx* c, const blz_scene_desc* d)
     }
     // Asynchronous with respect to the host when the sources are pinned; pageable sources are staged by the runtime before
     // cudaMemcpyAsync returns.  Either way the caller may reuse its arrays after blz_cull_synchronize().
+    if (c->optValidate) {
+        const int rc = validate_scene(c);                            // synchronises: the verdict is part of this call's return value
+        c->sceneRefused = rc != 0;                                   // every pass refuses to run on a malformed scene (check_list)
+        if (rc) return rc;
+    }
     return BLZ_OK;
 }
 
@@ -769,6 +832,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (strcmp(name, "early_auto") == 0) { c->optEarlyAuto = value; c->earlyDense = false; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     if (strcmp(name, "gather_tma") == 0) { c->optGatherTma = value; return BLZ_OK; }
+    if (strcmp(name, "validate_scene") == 0) { c->optValidate = value; return BLZ_OK; }
     if (strcmp(name, "epoch_wrap_at") == 0) { if (value < 4) return fail(BLZ_ERR_INVALID, "epoch_wrap_at < 4"); c->epochWrapAt = uint32_t(value); return BLZ_OK; }   // tests: restart the status tag every `value` launches
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);
 }

@@ -47,3 +47,36 @@ def test_misuse_is_reported_not_fatal(capi, small_scene):
         ctx.late(capi.REC_VK24, capi.HIZ_VK)
         _, tot_late = ctx.read_count()
         assert tot > 0 and tot_late == tot                             # frame 0: every frustum survivor is emitted
+
+
+def test_malformed_scene_is_refused(capi, small_scene):
+    """ids the kernels would index out of bounds with come back as an error from upload_scene; the context stays usable."""
+    sc = small_scene
+    ctx = capi.CullContext(0)
+    try:
+        bad = sc["objs"].copy()
+        bad["surfaceId"][123] = len(sc["surfaces"]) + 7
+        with pytest.raises(capi.BlzError, match="surfaceId"):
+            ctx.upload_scene(bad, sc["transforms"], sc["surfaces"], sc["lods"])
+        with pytest.raises(capi.BlzError):
+            ctx.frustum_lod()                                   # nothing runs on the refused scene
+        bad = sc["objs"].copy()
+        bad["transformId"][5] = len(sc["transforms"]) + 100
+        with pytest.raises(capi.BlzError, match="transformId"):
+            ctx.upload_scene(bad, sc["transforms"], sc["surfaces"], sc["lods"])
+        surf = sc["surfaces"].copy()
+        surf["lodOffset"][1] = len(sc["lods"])
+        with pytest.raises(capi.BlzError, match="LOD range"):
+            ctx.upload_scene(sc["objs"], sc["transforms"], surf, sc["lods"])
+        lods = sc["lods"].copy()
+        lods["clusterOffset"][3] = len(sc["clusters"]) + 1
+        with pytest.raises(capi.BlzError, match="cluster range"):
+            ctx.upload_scene(sc["objs"], sc["transforms"], sc["surfaces"], lods, clusters=sc["clusters"])
+        # a good scene afterwards: the context works
+        ctx.upload_scene(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"])
+        ctx.set_view(view_at(position=(380, 380, 380), z_far=2000.0))
+        ctx.frustum_lod()
+        _, total = ctx.read_draws()
+        assert total > 0
+    finally:
+        ctx.close()
