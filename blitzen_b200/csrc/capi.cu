@@ -160,6 +160,17 @@ int ensure_vis_words(blz_cull_ctx* c)
     return BLZ_OK;
 }
 
+// called by every pass that writes `draws`: after an asynchronous gather push flipped the buffers, the one about to be written may still be
+// read by its previous push (gather.cu)
+int acquire_draw_buffer(blz_cull_ctx* c)
+{
+    if (c->drawBufferPending) {
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->evPush[c->drawSlot], 0));
+        c->drawBufferPending = false;
+    }
+    return BLZ_OK;
+}
+
 int check_list(blz_cull_ctx* c, int list)
 {
     if (list < 0 || list > 2) return fail(BLZ_ERR_INVALID, "list %d out of range", list);
@@ -183,6 +194,7 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     DrawCullParams p{};
     p.objs = c->objs[list]; p.n = c->nObjs[list];
     p.xf = c->xf; p.surfaces = c->surf; p.lods = c->lods;
+    TRY_RC(acquire_draw_buffer(c));
     p.visibility = c->vis; p.draws = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
     p.numTiles = tiles_for(p.n);                      // re-derived from `items` by the launcher
     rc = ensure_status(c, p.n / kCullMinTile + 2u); if (rc) return rc;
@@ -644,6 +656,7 @@ int blz_cull_instanced(blz_cull_ctx* c, int list)
     q.list = c->survList; q.listCount = c->counts + 6; q.maxEntries = c->nObjs[list];
     q.lodInstances = c->lodInst; q.bucketCapacity = c->bucketCap; q.instanceIndices = c->instIdx;
     q.lods = c->lods; q.lodCount = c->nLods;
+    TRY_RC(acquire_draw_buffer(c));
     q.cmds = c->draws; q.counts = c->drawCounts; q.cmdCapacity = c->drawCap;
     q.hist = c->listScratch;
     CU_TRY(launch_list_instancing(q, c->stream));
@@ -684,6 +697,7 @@ int blz_cull_cluster_cull(blz_cull_ctx* c, int mode, int fmt, int hiz)
     ClusterCullParams p{};
     p.dispatch = c->dispatch; p.dispatchCount = c->counts + 2;
     p.objs = c->objs[BLZ_LIST_OPAQUE]; p.xf = c->xf; p.clusters = c->clusters;
+    TRY_RC(acquire_draw_buffer(c));
     p.draws = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
     p.maxRecords = uint32_t(c->dispatchCap > 0xFFFFFFFFull ? 0xFFFFFFFFull : c->dispatchCap);
     int rc = ensure_status(c, size_t(p.maxRecords) / kCullMinTile + 2u); if (rc) return rc;   // the kernel's tile is 512..1024 records (launch_cluster_cull)

@@ -75,6 +75,7 @@ struct blz_cull_ctx {
     blz::ExportableBuffer expDraws, expCounts; uint32_t exportGeneration = 0;
     cudaEvent_t exportFence = nullptr; void* extSemaphore = nullptr; bool extSemaphoreTimeline = false;
     cudaStream_t gatherStream = nullptr; cudaEvent_t evCull = nullptr, evPush[2] = { nullptr, nullptr }; bool evPushValid[2] = { false, false };
+    bool drawBufferPending = false;           // the current draw buffer's previous asynchronous push has not been waited for yet
 };
 
 namespace blz {

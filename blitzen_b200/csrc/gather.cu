@@ -383,7 +383,9 @@ int blz_cull_gather_push_async(blz_cull_ctx* c, uint32_t epoch)
     const uint32_t w = c->lastRecWords; c->lastRecWords = c->lastRecWordsAlt; c->lastRecWordsAlt = w;
     c->drawSlot ^= 1;
     c->drawCounts = c->counts + (c->drawSlot ? 8 : 0);
-    if (c->evPushValid[c->drawSlot]) CU_TRY(cudaStreamWaitEvent(c->stream, c->evPush[c->drawSlot], 0));   // that buffer's previous push
+    // the buffer the NEXT draw-writing pass will use may still be being pushed (its previous push): that pass waits for it when it starts
+    // (acquire_draw_buffer in capi.cu) -- not here, where the wait would also hold up passes that do not write draws (the pyramid build)
+    c->drawBufferPending = c->evPushValid[c->drawSlot];
     return BLZ_OK;
 }
 
