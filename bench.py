@@ -234,11 +234,11 @@ def main():
     epoch = [0]
 
     raster = args.depth == "raster"
-    # where the early list's push starts: behind the pyramid launch up to 4 ranks (the push then overlaps only the 175 us late pass and the
-    # 15 us pyramid build keeps the SMs' copy/store paths to itself), right behind the early pass beyond (the presenter ingests >= 75 MB per
-    # frame and needs more of the frame for it).  Measured, ms per frame (profiles/r02h_n8_ab.txt): N=2 0.2437 / 0.2573, N=4 0.2465 / 0.2668,
-    # N=8 0.3601 / 0.2933 (pyramid / early).  BLZ_PUSH_AFTER overrides.
-    push_early_first = os.environ.get("BLZ_PUSH_AFTER", "early" if world > 4 else "pyramid") == "early"
+    # where the early list's push starts: behind the pyramid launch (the push then overlaps only the 175 us late pass and the 15 us pyramid
+    # build keeps the SMs' copy/store paths to itself).  Measured at 2 / 4 / 8 GPUs against starting it right behind the early pass
+    # (profiles/r02h_n8_ab.txt): better or equal everywhere once the wait for a draw buffer's previous push sits in the pass that writes it.
+    # At 8 GPUs the frame is bound by the presenter's ingest either way.  BLZ_PUSH_AFTER=early|pyramid overrides.
+    push_early_first = os.environ.get("BLZ_PUSH_AFTER", "pyramid") == "early"
 
     # The early list is pushed by a throttled number of small co-resident CTAs (csrc/gather.cu) on a side stream; see push_early_first.
     def frame():
