@@ -196,6 +196,23 @@ int run_draw_pass(blz_cull_ctx* c, int pass, int list, int fmt, int hiz, uint32_
     p.xf = c->xf; p.surfaces = c->surf; p.lods = c->lods;
     TRY_RC(acquire_draw_buffer(c));
     p.visibility = c->vis; p.draws = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
+    // multi-GPU: the pass also leaves {objectId, lodId} per record for the gather to ship (8 bytes instead of 24 / 32 per record)
+    p.descs = nullptr;
+    if (c->gatherImported && c->optGatherDesc) {
+        const size_t need = size_t(c->drawCap) * sizeof(uint2) + 16u;
+        if (c->capDescs < need) {
+            CU_TRY(cudaStreamSynchronize(c->stream));
+            if (c->gatherStream) CU_TRY(cudaStreamSynchronize(c->gatherStream));
+            if (c->descs) cudaFree(c->descs);
+            if (c->descsAlt) cudaFree(c->descsAlt);
+            c->descs = c->descsAlt = nullptr; c->capDescs = 0;
+            CU_TRY(cudaMalloc(&c->descs, need));
+            CU_TRY(cudaMalloc(&c->descsAlt, need));
+            c->capDescs = need;
+        }
+        p.descs = c->descs;
+    }
+    c->descValid = p.descs != nullptr;
     p.numTiles = tiles_for(p.n);                      // re-derived from `items` by the launcher
     rc = ensure_status(c, p.n / kCullMinTile + 2u); if (rc) return rc;
     p.status = c->status;
@@ -329,6 +346,7 @@ static void free_scene(blz_cull_ctx* c)
     dfree(c->xf); c->nXf = 0;
     dfree(c->surf); dfree(c->lods); dfree(c->clusters); dfree(c->lodInst); dfree(c->bucketCap);
     if (c->expDraws.active) { blz::exportable_free(c->expDraws); c->draws = nullptr; }
+    dfree(c->descs); dfree(c->descsAlt); c->capDescs = 0; c->descValid = c->descValidAlt = false;
     dfree(c->vis); dfree(c->visBits); dfree(c->draws); dfree(c->drawsAlt); dfree(c->dispatch); dfree(c->instIdx); dfree(c->survList); dfree(c->listScratch); c->capSurvList = 0; c->capListScratch = 0;
     c->capVisBits = 0; c->visBitsValid = false;
     c->nSurf = c->nLods = c->nClusters = c->nLodInst = 0; c->drawCap = c->dispatchCap = c->instCap = 0;
@@ -657,6 +675,7 @@ int blz_cull_instanced(blz_cull_ctx* c, int list)
     q.lodInstances = c->lodInst; q.bucketCapacity = c->bucketCap; q.instanceIndices = c->instIdx;
     q.lods = c->lods; q.lodCount = c->nLods;
     TRY_RC(acquire_draw_buffer(c));
+    c->descValid = false;
     q.cmds = c->draws; q.counts = c->drawCounts; q.cmdCapacity = c->drawCap;
     q.hist = c->listScratch;
     CU_TRY(launch_list_instancing(q, c->stream));
@@ -698,6 +717,7 @@ int blz_cull_cluster_cull(blz_cull_ctx* c, int mode, int fmt, int hiz)
     p.dispatch = c->dispatch; p.dispatchCount = c->counts + 2;
     p.objs = c->objs[BLZ_LIST_OPAQUE]; p.xf = c->xf; p.clusters = c->clusters;
     TRY_RC(acquire_draw_buffer(c));
+    c->descValid = false;
     p.draws = c->draws; p.counts = c->drawCounts; p.ctl = c->ctl;
     p.maxRecords = uint32_t(c->dispatchCap > 0xFFFFFFFFull ? 0xFFFFFFFFull : c->dispatchCap);
     int rc = ensure_status(c, size_t(p.maxRecords) / kCullMinTile + 2u); if (rc) return rc;   // the kernel's tile is 512..1024 records (launch_cluster_cull)
@@ -846,6 +866,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (strcmp(name, "early_auto") == 0) { c->optEarlyAuto = value; c->earlyDense = false; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     if (strcmp(name, "gather_tma") == 0) { c->optGatherTma = value; return BLZ_OK; }
+    if (strcmp(name, "gather_desc") == 0) { c->optGatherDesc = value; return BLZ_OK; }
     if (strcmp(name, "validate_scene") == 0) { c->optValidate = value; return BLZ_OK; }
     if (strcmp(name, "epoch_wrap_at") == 0) { if (value < 4) return fail(BLZ_ERR_INVALID, "epoch_wrap_at < 4"); c->epochWrapAt = uint32_t(value); return BLZ_OK; }   // tests: restart the status tag every `value` launches
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);

@@ -69,12 +69,17 @@ struct blz_cull_ctx {
     uint32_t* gatherDst = nullptr; uint64_t* gatherDstFlags = nullptr; int rank = 0, world = 1; bool gatherImported = false, gatherPeerMapped = false;
     uint32_t* gatherDone = nullptr;
     uint32_t* instDst = nullptr; bool instDstMapped = false;   // presenter's instance index buffer (instance-list gather)
+    // descriptor transport (gather.cu): the draw passes also write {objectId, lodId} per record; the ranks ship those 8 bytes instead of the 24/32-byte
+    // records and the presenter expands them with its own LOD table.  descs / descsAlt flip together with draws / drawsAlt.
+    uint2* descs = nullptr; uint2* descsAlt = nullptr; size_t capDescs = 0; bool descValid = false, descValidAlt = false;
+    int64_t optGatherDesc = 1;
     // asynchronous push: the list just pushed stays readable in `drawsAlt` while the next pass writes `draws` (blz_cull_gather_push_async)
     uint32_t* drawsAlt = nullptr; uint32_t lastRecWordsAlt = 6; int drawSlot = 0;
     // zero-copy export of the outputs (interop.cu): when active, `draws` / `counts` live in these allocations instead of cudaMalloc memory
     blz::ExportableBuffer expDraws, expCounts; uint32_t exportGeneration = 0;
     cudaEvent_t exportFence = nullptr; void* extSemaphore = nullptr; bool extSemaphoreTimeline = false;
     cudaStream_t gatherStream = nullptr; cudaEvent_t evCull = nullptr, evPush[2] = { nullptr, nullptr }; bool evPushValid[2] = { false, false };
+    cudaEvent_t evExpand = nullptr; bool evExpandValid = false;    // descriptor mode, presenter: behind the expansion of the last asynchronous push
     bool drawBufferPending = false;           // the current draw buffer's previous asynchronous push has not been waited for yet
 };
 

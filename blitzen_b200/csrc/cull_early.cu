@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(kEsThreads, BITS ? 3 : 4) early_stream_kernel(
                 const uint32_t d = s_stage[f2Slot][r];
                 const uint2 L = __ldg(reinterpret_cast<const uint2*>(p.lods + (d >> kEsLocalBits)));       // {indexCount, firstIndex}
                 st_cs_u2(dst + w, f == 0u ? make_uint2(idBase + (d & ((1u << kEsLocalBits) - 1u)), L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
+                if (f == 2u && p.descs != nullptr) st_cs_u2(p.descs + prefix + r, make_uint2(idBase + (d & ((1u << kEsLocalBits) - 1u)), d >> kEsLocalBits));
             }
             cum = prefix + f2Total;
             nextRead = f2Tile + 1u;

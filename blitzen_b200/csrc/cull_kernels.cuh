@@ -21,6 +21,7 @@ struct DrawCullParams {
     uint32_t* counts;                // [0] = written (clamped to capacity), [1] = total
     uint32_t* visTotal;              // pipelined early pass: += number of previously-visible objects it walked (may be null) ...
     uint32_t* visTotalOut;           // ... and the last CTA out stores the total here (host-mapped pinned word) and zeroes the accumulator
+    uint2* descs;                    // optional (may be null): {objectId, absolute LOD id} of every record written, same order and clamp -- what the multi-GPU gather ships instead of the 24/32-byte records
     uint32_t* visBits;               // 1 bit per object (word i = objects 32i..32i+31): written by the streaming late pass, source of the pipelined early pass (may be null)
     // scan state
     ScanCtl* ctl;

@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
                         const uint32_t d = st[r];
                         const uint2 L = *reinterpret_cast<const uint2*>(&lodT[d >> kSLocalBits]);    // {indexCount, firstIndex}
                         st_rec_u2(dst + w, f == 0u ? make_uint2(idBase + (d & kSLocalMask), L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
+                        if (f == 2u && p.descs != nullptr) st_rec_u2(p.descs + prefix + r, make_uint2(idBase + (d & kSLocalMask), d >> kSLocalBits));
                     }
                 } else {
                     for (uint32_t w = tid; w < nrec * 4u; w += THREADS) {
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(THREADS, MINB) stream_cull_kernel(const __grid
                         const uint32_t d = st[r];
                         const uint2 L = *reinterpret_cast<const uint2*>(&lodT[d >> kSLocalBits]);
                         st_rec_u2(dst + w, f == 0u ? make_uint2(idBase + (d & kSLocalMask), L.x) : (f == 1u ? make_uint2(1u, L.y) : make_uint2(0u, 0u)));
+                        if (f == 3u && p.descs != nullptr) st_rec_u2(p.descs + prefix + r, make_uint2(idBase + (d & kSLocalMask), d >> kSLocalBits));
                     }
                 }
             }

@@ -41,6 +41,7 @@ struct GatherParams {
     uint32_t* done;                                  // local CTA-completion counter (self-resetting)
     uint64_t capacity;                               // records the presenter's buffer holds
     uint32_t recWords, rank, world, epoch;
+    uint32_t signalDone;                             // 0 on the presenter in descriptor mode: its done flag is raised by gather_expand_kernel
 };
 
 template <int THREADS>
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(THREADS) gather_push_kernel(const GatherParams
         const uint32_t prev = atomicAdd(p.done, 1u);
         if (prev == gridDim.x - 1u) {
             *p.done = 0u;
-            st_release_sys_u64(p.flags + kDoneRow * kFlagStride + p.rank, uint64_t(p.epoch));
+            if (p.signalDone) st_release_sys_u64(p.flags + kDoneRow * kFlagStride + p.rank, uint64_t(p.epoch));
         }
     }
 }
@@ -190,6 +191,78 @@ __global__ void __launch_bounds__(kPushThreads) gather_push_tma_kernel(const Gat
         const uint32_t prev = atomicAdd(p.done, 1u);
         if (prev == gridDim.x - 1u) {
             *p.done = 0u;
+            if (p.signalDone) st_release_sys_u64(p.flags + kDoneRow * kFlagStride + p.rank, uint64_t(p.epoch));
+        }
+    }
+}
+
+// Descriptor transport, presenter side.  The ranks shipped {objectId, absolute LOD id} (8 bytes) per record into the descriptor area of the gather
+// buffer, concatenated in rank order exactly like records; this kernel waits until every OTHER rank's push of `epoch` has landed (done flags; the
+// presenter's own push precedes it on the stream), then expands descriptor r into record r of the record area with the presenter's own LOD table --
+// the table is replicated, so the result is byte for byte what the ranks' own passes wrote locally:
+// {objectId, indexCount, 1, firstIndex, 0, 0 [, 0, 0]}.  The presenter's done flag of the epoch is raised HERE (last CTA out), not by its push:
+// "every rank is done with epoch e" then also means "the descriptors of e have been read", which is what lets the ranks overwrite that half of the
+// descriptor area with epoch e + 2 (back-pressure in the push kernel).  Same small shape as the push (64 threads, <= 1 CTA per SM, no shared memory
+// to speak of) so that it runs next to the persistent cull kernels; 8 records in flight per thread (one record per round trip measured 0.4 ms for
+// 1.2 M records: latency-bound).  8 GPUs: the presenter ingests 35 MB instead of 105 MB per frame.
+struct ExpandParams {
+    const uint2* descs; uint32_t* records; uint64_t* flags; const LodData* lods; uint32_t* done; uint32_t lodCount;
+    uint64_t capacity; uint32_t recWords, world, rank, epoch;
+};
+constexpr int kExpandThreads = 64;
+constexpr int kExpandInFlight = 8;
+
+template <int RECW2>     // uint2 words per record: 3 (VK24) or 4 (DX32)
+__device__ __forceinline__ void expand_store(uint2* out, uint64_t r, uint2 d, uint2 L, bool ok)
+{
+    uint2* o = out + r * uint64_t(RECW2);
+    const uint2 a = ok ? make_uint2(d.x, L.x) : make_uint2(0u, 0u), b = ok ? make_uint2(1u, L.y) : make_uint2(0u, 0u);
+    asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(o), "r"(a.x), "r"(a.y) : "memory");
+    asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(o + 1), "r"(b.x), "r"(b.y) : "memory");
+#pragma unroll
+    for (int f = 2; f < RECW2; ++f) asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(o + f), "r"(0u), "r"(0u) : "memory");
+}
+
+template <int RECW2>
+__global__ void __launch_bounds__(kExpandThreads) gather_expand_kernel(const ExpandParams p)
+{
+    __shared__ uint64_t s_total;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        uint64_t total = 0;
+        for (uint32_t r = 0; r < p.world; ++r) {
+            if (r != p.rank) while (int32_t(uint32_t(ld_acquire_sys_u64(p.flags + kDoneRow * kFlagStride + r)) - p.epoch) < 0) { }
+            total += uint32_t(ld_acquire_sys_u64(p.flags + (p.epoch % uint32_t(kEpochSlots)) * kFlagStride + r));
+        }
+        s_total = total < p.capacity ? total : p.capacity;
+    }
+    __syncthreads();
+    const uint64_t n = s_total;
+    uint2* out = reinterpret_cast<uint2*>(p.records);
+    const uint64_t stride = uint64_t(gridDim.x) * kExpandThreads;
+    uint64_t r = uint64_t(blockIdx.x) * kExpandThreads + tid;
+    for (; r + uint64_t(kExpandInFlight - 1) * stride < n; r += uint64_t(kExpandInFlight) * stride) {
+        uint2 d[kExpandInFlight], L[kExpandInFlight];
+#pragma unroll
+        for (int u = 0; u < kExpandInFlight; ++u) asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(d[u].x), "=r"(d[u].y) : "l"(p.descs + r + uint64_t(u) * stride));   // written by peers: L2, never L1
+#pragma unroll
+        for (int u = 0; u < kExpandInFlight; ++u) L[u] = __ldg(reinterpret_cast<const uint2*>(p.lods + (d[u].y < p.lodCount ? d[u].y : 0u)));                                // {indexCount, firstIndex}
+#pragma unroll
+        for (int u = 0; u < kExpandInFlight; ++u) expand_store<RECW2>(out, r + uint64_t(u) * stride, d[u], L[u], d[u].y < p.lodCount);
+    }
+    for (; r < n; r += stride) {
+        uint2 d;
+        asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(d.x), "=r"(d.y) : "l"(p.descs + r));
+        const bool ok = d.y < p.lodCount;
+        const uint2 L = __ldg(reinterpret_cast<const uint2*>(p.lods + (ok ? d.y : 0u)));
+        expand_store<RECW2>(out, r, d, L, ok);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t prev = atomicAdd(p.done, 1u);
+        if (prev == gridDim.x - 1u) {
+            *p.done = 0u;
             st_release_sys_u64(p.flags + kDoneRow * kFlagStride + p.rank, uint64_t(p.epoch));
         }
     }
@@ -250,7 +323,7 @@ void gather_release(blz_cull_ctx* c)
     if (c->instDstMapped && c->instDst) cudaIpcCloseMemHandle(c->instDst);
     c->instDst = nullptr; c->instDstMapped = false;
     if (c->gatherDone) cudaFree(c->gatherDone);
-    if (c->gatherStream) { cudaStreamSynchronize(c->gatherStream); cudaStreamDestroy(c->gatherStream); cudaEventDestroy(c->evCull); cudaEventDestroy(c->evPush[0]); cudaEventDestroy(c->evPush[1]); c->gatherStream = nullptr; c->evPushValid[0] = c->evPushValid[1] = false; }
+    if (c->gatherStream) { cudaStreamSynchronize(c->gatherStream); cudaStreamDestroy(c->gatherStream); cudaEventDestroy(c->evCull); cudaEventDestroy(c->evPush[0]); cudaEventDestroy(c->evPush[1]); cudaEventDestroy(c->evExpand); c->evExpandValid = false; c->gatherStream = nullptr; c->evPushValid[0] = c->evPushValid[1] = false; }
     c->gatherBuf = nullptr; c->gatherFlags = nullptr; c->gatherDst = nullptr; c->gatherDstFlags = nullptr; c->gatherDone = nullptr;
     c->gatherOwner = c->gatherImported = c->gatherPeerMapped = false;
 }
@@ -269,7 +342,8 @@ int blz_cull_gather_export(blz_cull_ctx* c, uint64_t capacityRecords, int fmt, v
     gather_release(c);
     c->gatherRecWords = fmt == BLZ_REC_VK24 ? 6u : 8u;
     c->gatherCap = capacityRecords;
-    CU_TRY(cudaMalloc(&c->gatherBuf, 2u * size_t(capacityRecords) * c->gatherRecWords * 4u));   // two halves: epoch parity
+    // two halves (epoch parity) of records, then two halves of 8-byte descriptors (descriptor transport) in the SAME allocation: one IPC handle
+    CU_TRY(cudaMalloc(&c->gatherBuf, 2u * size_t(capacityRecords) * c->gatherRecWords * 4u + 2u * size_t(capacityRecords) * 8u));
     CU_TRY(cudaMalloc(&c->gatherFlags, kFlagWords * sizeof(uint64_t)));
     CU_TRY(cudaMemset(c->gatherFlags, 0, kFlagWords * sizeof(uint64_t)));
     c->gatherOwner = true;
@@ -300,8 +374,8 @@ int blz_cull_gather_import(blz_cull_ctx* c, const void* blob128, int rank, int w
         c->gatherDst = static_cast<uint32_t*>(a); c->gatherDstFlags = static_cast<uint64_t*>(b); c->gatherPeerMapped = true;
     }
     if (!c->gatherDone) {
-        CU_TRY(cudaMalloc(&c->gatherDone, sizeof(uint32_t)));
-        CU_TRY(cudaMemset(c->gatherDone, 0, sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&c->gatherDone, 2 * sizeof(uint32_t)));          // CTA-completion counters: [0] push, [1] expansion (self-resetting)
+        CU_TRY(cudaMemset(c->gatherDone, 0, 2 * sizeof(uint32_t)));
     }
     c->gatherImported = true;
     return BLZ_OK;
@@ -315,16 +389,37 @@ int blz_cull_gather_configure(blz_cull_ctx* c, uint64_t capacityRecords, int fmt
     return BLZ_OK;
 }
 
+static bool gather_desc_mode(const blz_cull_ctx* c) { return c->descValid && c->optGatherDesc != 0; }   // every rank runs the same pass sequence with the same options: the mode is uniform
+
 static int gather_launch(blz_cull_ctx* c, uint32_t epoch, cudaStream_t stream, int grid)
 {
     GatherParams p{};
-    p.src = c->draws; p.srcCount = c->drawCounts; p.flags = c->gatherDstFlags; p.done = c->gatherDone;
-    p.dst = c->gatherDst + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords;
-    p.capacity = c->gatherCap; p.recWords = c->gatherRecWords; p.rank = uint32_t(c->rank); p.world = uint32_t(c->world); p.epoch = epoch;
+    const bool desc = gather_desc_mode(c);
+    uint32_t* descArea = c->gatherDst + 2u * size_t(c->gatherCap) * c->gatherRecWords;   // behind the two record halves (8-byte aligned: recWords is even)
+    p.src = desc ? reinterpret_cast<const uint32_t*>(c->descs) : c->draws; p.srcCount = c->drawCounts; p.flags = c->gatherDstFlags; p.done = c->gatherDone;
+    p.recWords = desc ? 2u : c->gatherRecWords;
+    p.dst = desc ? descArea + size_t(epoch & 1u) * c->gatherCap * 2u : c->gatherDst + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords;
+    p.capacity = c->gatherCap; p.rank = uint32_t(c->rank); p.world = uint32_t(c->world); p.epoch = epoch;
+    p.signalDone = (desc && c->gatherOwner) ? 0u : 1u;
     const int perSM = grid > 0 && grid < c->numSMs ? grid : c->numSMs;             // the co-resident forms: one small CTA per SM at most
     if (c->optGatherTma == 1) gather_push_tma_kernel<<<perSM, kPushThreads, kPushStages * kPushChunk, stream>>>(p);
     else if (c->optGatherTma == 2) gather_push_kernel<kPushThreads><<<perSM, kPushThreads, 0, stream>>>(p);
     else gather_push_kernel<kGatherThreads><<<grid, kGatherThreads, 0, stream>>>(p);
+    CU_TRY(cudaGetLastError());
+    c->launches++;
+    return BLZ_OK;
+}
+
+// descriptor mode, presenter only: expands what everybody shipped for `epoch` (behind the presenter's own push on the same stream)
+static int gather_expand_launch(blz_cull_ctx* c, uint32_t epoch, cudaStream_t stream)
+{
+    ExpandParams e{};
+    e.descs = reinterpret_cast<const uint2*>(c->gatherBuf + 2u * size_t(c->gatherCap) * c->gatherRecWords) + size_t(epoch & 1u) * c->gatherCap;
+    e.records = c->gatherBuf + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords;
+    e.flags = c->gatherFlags; e.lods = c->lods; e.lodCount = c->nLods; e.capacity = c->gatherCap; e.recWords = c->gatherRecWords;
+    e.done = c->gatherDone + 1; e.world = uint32_t(c->world); e.rank = uint32_t(c->rank); e.epoch = epoch;
+    if (c->gatherRecWords == 6u) gather_expand_kernel<3><<<c->numSMs, kExpandThreads, 0, stream>>>(e);
+    else gather_expand_kernel<4><<<c->numSMs, kExpandThreads, 0, stream>>>(e);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return BLZ_OK;
@@ -342,7 +437,12 @@ int blz_cull_gather_push(blz_cull_ctx* c, uint32_t epoch)
 {
     int rc = gather_check(c, epoch); if (rc) return rc;
     CU_TRY(cudaSetDevice(c->device));
-    return gather_launch(c, epoch, c->stream, c->numSMs * 2);
+    // the push / expansion kernels share their CTA-completion counters with the asynchronous form: order this push behind whatever the side stream still runs
+    for (int k = 0; k < 2; ++k) if (c->evPushValid[k]) CU_TRY(cudaStreamWaitEvent(c->stream, c->evPush[k], 0));
+    if (c->evExpandValid) CU_TRY(cudaStreamWaitEvent(c->stream, c->evExpand, 0));
+    const bool expand = gather_desc_mode(c) && c->gatherOwner;
+    rc = gather_launch(c, epoch, c->stream, c->numSMs * 2); if (rc) return rc;
+    return expand ? gather_expand_launch(c, epoch, c->stream) : BLZ_OK;
 }
 
 // Same push, off the critical path: it runs on a side stream behind the pass that produced the list, and the context flips to its
@@ -358,6 +458,7 @@ int blz_cull_gather_push_async(blz_cull_ctx* c, uint32_t epoch)
         CU_TRY(cudaEventCreateWithFlags(&c->evCull, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&c->evPush[0], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&c->evPush[1], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->evExpand, cudaEventDisableTiming));
     }
     if (c->expDraws.active) return fail(BLZ_ERR_STATE, "asynchronous pushes alternate two draw buffers: not available once the outputs have been exported");
     if (!c->drawsAlt) CU_TRY(cudaMalloc(&c->drawsAlt, c->capDraws));
@@ -376,10 +477,18 @@ int blz_cull_gather_push_async(blz_cull_ctx* c, uint32_t epoch)
         ctas = ctas < 4 ? 4 : (ctas > 32 ? 32 : ctas);
     }
     if (envCtas > 0) ctas = envCtas;
+    const bool expand = gather_desc_mode(c) && c->gatherOwner;
     rc = gather_launch(c, epoch, c->gatherStream, ctas); if (rc) return rc;
-    CU_TRY(cudaEventRecord(c->evPush[c->drawSlot], c->gatherStream));
+    CU_TRY(cudaEventRecord(c->evPush[c->drawSlot], c->gatherStream));      // the draw (and descriptor) buffer of this slot is free again from here on
     c->evPushValid[c->drawSlot] = true;
+    if (expand) {
+        // the presenter's expansion waits for the OTHER ranks' pushes: it must not sit in front of evPush, or the presenter's next pass would wait for them too
+        rc = gather_expand_launch(c, epoch, c->gatherStream); if (rc) return rc;
+        CU_TRY(cudaEventRecord(c->evExpand, c->gatherStream));
+        c->evExpandValid = true;
+    }
     uint32_t* t = c->draws; c->draws = c->drawsAlt; c->drawsAlt = t;
+    { uint2* d = c->descs; c->descs = c->descsAlt; c->descsAlt = d; const bool v = c->descValid; c->descValid = c->descValidAlt; c->descValidAlt = v; }
     const uint32_t w = c->lastRecWords; c->lastRecWords = c->lastRecWordsAlt; c->lastRecWordsAlt = w;
     c->drawSlot ^= 1;
     c->drawCounts = c->counts + (c->drawSlot ? 8 : 0);
@@ -395,6 +504,7 @@ int blz_cull_gather_join(blz_cull_ctx* c)
     if (!c) return fail(BLZ_ERR_INVALID, "null context");
     CU_TRY(cudaSetDevice(c->device));
     for (int k = 0; k < 2; ++k) if (c->evPushValid[k]) CU_TRY(cudaStreamWaitEvent(c->stream, c->evPush[k], 0));
+    if (c->evExpandValid) CU_TRY(cudaStreamWaitEvent(c->stream, c->evExpand, 0));
     return BLZ_OK;
 }
 
@@ -402,6 +512,7 @@ int blz_cull_gather_read(blz_cull_ctx* c, uint32_t epoch, void* recordsHost, uin
 {
     if (!c || !c->gatherOwner) return fail(BLZ_ERR_INVALID, "only the presenting rank (the exporter) can read the gathered list");
     CU_TRY(cudaSetDevice(c->device));
+    if (c->evExpandValid) CU_TRY(cudaStreamWaitEvent(c->stream, c->evExpand, 0));   // asynchronous pushes in descriptor mode: the expansion runs on the side stream
     gather_wait_kernel<<<1, kFlagStride, 0, c->stream>>>(c->gatherFlags, uint32_t(c->world), epoch);
     CU_TRY(cudaGetLastError());
     c->launches++;
