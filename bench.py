@@ -238,7 +238,7 @@ def main():
     # build keeps the SMs' copy/store paths to itself).  Measured at 2 / 4 / 8 GPUs against starting it right behind the early pass
     # (profiles/r02h_n8_ab.txt): better or equal everywhere once the wait for a draw buffer's previous push sits in the pass that writes it.
     # At 8 GPUs the frame is bound by the presenter's ingest either way.  BLZ_PUSH_AFTER=early|pyramid overrides.
-    push_early_first = os.environ.get("BLZ_PUSH_AFTER", "pyramid") == "early"
+    push_early_first = os.environ.get("BLZ_PUSH_AFTER", "early" if world > 4 else "pyramid") == "early"
 
     # The early list is pushed by a throttled number of small co-resident CTAs (csrc/gather.cu) on a side stream; see push_early_first.
     def frame():

@@ -205,6 +205,10 @@ __global__ void __launch_bounds__(kPushThreads) gather_push_tma_kernel(const Gat
 // descriptor area with epoch e + 2 (back-pressure in the push kernel).  Same small shape as the push (64 threads, <= 1 CTA per SM, no shared memory
 // to speak of) so that it runs next to the persistent cull kernels; 8 records in flight per thread (one record per round trip measured 0.4 ms for
 // 1.2 M records: latency-bound).  8 GPUs: the presenter ingests 35 MB instead of 105 MB per frame.
+// It must stay at 32 registers and (next to) no shared memory: 64 threads x 32 registers is what fits beside the push kernel in the 4 096 registers
+// the persistent cull kernels leave free per SM, and shared memory beyond the cull kernels' carve-out makes its CTAs wait for a cull kernel to END --
+// a variant with the LOD table staged in 8 KB of shared memory measured 0.89 ms per frame at 8 GPUs instead of 0.276 (profiles/r02l_n8_desc.txt).
+// The expansion has to keep up with the frame: 48 CTAs instead of 148 measured 0.45 ms per frame (the next list's push queues behind it).
 struct ExpandParams {
     const uint2* descs; uint32_t* records; uint64_t* flags; const LodData* lods; uint32_t* done; uint32_t lodCount;
     uint64_t capacity; uint32_t recWords, world, rank, epoch;
@@ -227,6 +231,7 @@ template <int RECW2>
 __global__ void __launch_bounds__(kExpandThreads) gather_expand_kernel(const ExpandParams p)
 {
     __shared__ uint64_t s_total;
+    constexpr int kInFlight = RECW2 == 3 ? kExpandInFlight : kExpandInFlight - 2;    // DX32: 6, which keeps the kernel at 32 registers like the VK24 form
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         uint64_t total = 0;
@@ -241,14 +246,14 @@ __global__ void __launch_bounds__(kExpandThreads) gather_expand_kernel(const Exp
     uint2* out = reinterpret_cast<uint2*>(p.records);
     const uint64_t stride = uint64_t(gridDim.x) * kExpandThreads;
     uint64_t r = uint64_t(blockIdx.x) * kExpandThreads + tid;
-    for (; r + uint64_t(kExpandInFlight - 1) * stride < n; r += uint64_t(kExpandInFlight) * stride) {
-        uint2 d[kExpandInFlight], L[kExpandInFlight];
+    for (; r + uint64_t(kInFlight - 1) * stride < n; r += uint64_t(kInFlight) * stride) {
+        uint2 d[kInFlight], L[kInFlight];
 #pragma unroll
-        for (int u = 0; u < kExpandInFlight; ++u) asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(d[u].x), "=r"(d[u].y) : "l"(p.descs + r + uint64_t(u) * stride));   // written by peers: L2, never L1
+        for (int u = 0; u < kInFlight; ++u) asm volatile("ld.global.cg.v2.u32 {%0, %1}, [%2];" : "=r"(d[u].x), "=r"(d[u].y) : "l"(p.descs + r + uint64_t(u) * stride));   // written by peers: L2, never L1
 #pragma unroll
-        for (int u = 0; u < kExpandInFlight; ++u) L[u] = __ldg(reinterpret_cast<const uint2*>(p.lods + (d[u].y < p.lodCount ? d[u].y : 0u)));                                // {indexCount, firstIndex}
+        for (int u = 0; u < kInFlight; ++u) L[u] = __ldg(reinterpret_cast<const uint2*>(p.lods + (d[u].y < p.lodCount ? d[u].y : 0u)));                                // {indexCount, firstIndex}
 #pragma unroll
-        for (int u = 0; u < kExpandInFlight; ++u) expand_store<RECW2>(out, r + uint64_t(u) * stride, d[u], L[u], d[u].y < p.lodCount);
+        for (int u = 0; u < kInFlight; ++u) expand_store<RECW2>(out, r + uint64_t(u) * stride, d[u], L[u], d[u].y < p.lodCount);
     }
     for (; r < n; r += stride) {
         uint2 d;
@@ -418,8 +423,10 @@ static int gather_expand_launch(blz_cull_ctx* c, uint32_t epoch, cudaStream_t st
     e.records = c->gatherBuf + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords;
     e.flags = c->gatherFlags; e.lods = c->lods; e.lodCount = c->nLods; e.capacity = c->gatherCap; e.recWords = c->gatherRecWords;
     e.done = c->gatherDone + 1; e.world = uint32_t(c->world); e.rank = uint32_t(c->rank); e.epoch = epoch;
-    if (c->gatherRecWords == 6u) gather_expand_kernel<3><<<c->numSMs, kExpandThreads, 0, stream>>>(e);
-    else gather_expand_kernel<4><<<c->numSMs, kExpandThreads, 0, stream>>>(e);
+    static const int envCtas = [] { const char* v = getenv("BLZ_EXPAND_CTAS"); return v ? atoi(v) : 0; }();   // measurement aid
+    const int grid = envCtas > 0 && envCtas < c->numSMs ? envCtas : c->numSMs;                                // one small co-resident CTA per SM at most
+    if (c->gatherRecWords == 6u) gather_expand_kernel<3><<<grid, kExpandThreads, 0, stream>>>(e);
+    else gather_expand_kernel<4><<<grid, kExpandThreads, 0, stream>>>(e);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return BLZ_OK;

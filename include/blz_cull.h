@@ -205,7 +205,13 @@ int blz_cull_consume_gathered(blz_cull_ctx* ctx, uint32_t epoch, blz_consume_sum
  *                            gather buffer at that offset over NVLink peer memory.  No NCCL call on the data path.
  *                            `epoch` = 1, 2, 3, ... (consecutive, the same sequence on every rank).  Ranks need no host-side
  *                            ordering between pushes: counts are kept per epoch in a ring of 4 and a rank stalls (on the
- *                            device) rather than run more than 3 epochs ahead of the slowest one. */
+ *                            device) rather than run more than 3 epochs ahead of the slowest one.
+ *   Transport (option "gather_desc", default 1): behind an object-list pass (early / late / temporal / frustum) the ranks ship 8-byte
+ *   {objectId, absolute LOD id} descriptors instead of the 24-/32-byte records and the presenter expands them with its own (replicated)
+ *   LOD table into the same record area, behind its own push -- a third of the bytes into the one GPU that ingests everything; the
+ *   gathered list is byte-identical either way and is complete once every rank's done flag carries the epoch (the presenter raises its
+ *   own after the expansion: blz_cull_gather_read / blz_cull_consume_gathered / blz_cull_gather_join wait for it).  Cluster draw lists
+ *   always travel as records. */
 int blz_cull_gather_export(blz_cull_ctx* ctx, uint64_t capacity_records, int record_format, void* out_blob128);
 int blz_cull_gather_import(blz_cull_ctx* ctx, const void* presenter_blob128, int rank, int world);
 /* ranks that did not export learn the presenter buffer's capacity / record format from the host layer */
