@@ -865,7 +865,6 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     }
     if (strcmp(name, "early_auto") == 0) { c->optEarlyAuto = value; c->earlyDense = false; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
-    if (strcmp(name, "gather_tma") == 0) { c->optGatherTma = value; return BLZ_OK; }
     if (strcmp(name, "gather_desc") == 0) { c->optGatherDesc = value; return BLZ_OK; }
     if (strcmp(name, "validate_scene") == 0) { c->optValidate = value; return BLZ_OK; }
     if (strcmp(name, "epoch_wrap_at") == 0) { if (value < 4) return fail(BLZ_ERR_INVALID, "epoch_wrap_at < 4"); c->epochWrapAt = uint32_t(value); return BLZ_OK; }   // tests: restart the status tag every `value` launches

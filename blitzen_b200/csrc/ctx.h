@@ -61,7 +61,6 @@ struct blz_cull_ctx {
     int64_t optEarlyAuto = 1;                 // early_mode 1: switch to the streaming kernel while more than ~20 % of the objects were visible last frame
     bool sceneRefused = false;                // the last upload_scene failed validation
     int64_t optValidate = 1;                  // upload_scene checks every id the kernels will index with (one pass + one 16-byte read-back)
-    int64_t optGatherTma = 2;                 // draw-list push: 2 = 64-thread co-resident CTAs, register stores (default); 1 = same shape, TMA bulk stores; 0 = 256-thread CTAs (r01)
     int64_t optStreamCfg = 2;                 // CTA shape of the streaming kernel (see launch_pass in cull_stream.cu)
     uint32_t lastRecWords = 6;                // record width (u32 words) of the pass that last wrote `draws`
     // gather (multi-GPU): the presenter owns gatherBuf/gatherFlags; every rank (presenter included) writes through gatherDst*

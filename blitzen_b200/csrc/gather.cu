@@ -44,10 +44,11 @@ struct GatherParams {
     uint32_t signalDone;                             // 0 on the presenter in descriptor mode: its done flag is raised by gather_expand_kernel
 };
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) gather_push_kernel(const GatherParams p)
+// 64 threads, 32 registers, no shared memory to speak of: at most one CTA per SM, which fits in what the persistent cull kernels leave free
+// (a 256-thread shape sat idle until the NEXT cull pass had finished: kernel timeline of the 2-GPU frame, profiles/r02g_trace_n2.txt)
+constexpr int kPushThreads = 64;
+__global__ void __launch_bounds__(kPushThreads) gather_push_kernel(const GatherParams p)
 {
-    constexpr int kGatherThreads = THREADS;      // shadows the file-level default inside this kernel
     __shared__ uint64_t s_off;
     const uint32_t tid = threadIdx.x;
     uint32_t count;
@@ -77,8 +78,8 @@ __global__ void __launch_bounds__(THREADS) gather_push_kernel(const GatherParams
     uint2* dst = reinterpret_cast<uint2*>(p.dst + off * p.recWords);
     // eight independent loads in flight per thread: with one, a CTA moves 256 x 8 B per local-memory round trip (measured 3.7 GB/s per
     // CTA -- the push was load-latency-bound, not NVLink-bound)
-    const uint64_t stride = uint64_t(gridDim.x) * kGatherThreads;
-    uint64_t j = uint64_t(blockIdx.x) * kGatherThreads + tid;
+    const uint64_t stride = uint64_t(gridDim.x) * kPushThreads;
+    uint64_t j = uint64_t(blockIdx.x) * kPushThreads + tid;
     for (; j + 7ull * stride < n64; j += 8ull * stride) {
         uint2 v[8];
 #pragma unroll
@@ -98,103 +99,10 @@ __global__ void __launch_bounds__(THREADS) gather_push_kernel(const GatherParams
     }
 }
 
-// ---- the same push with TMA bulk stores (option gather_tma = 1) -------------------------------------------------------------------------------------------
-// The kernel above stores over NVLink from registers: its CTAs hold LSU store slots while the link drains and, worse, they cannot start at all
-// next to the persistent cull kernels (which fill every SM's register file), so a push issued behind a pass sat idle until the NEXT pass had
-// finished -- the trace of a 2-GPU frame (scripts/trace_frames.py) shows the empty late-list push taking 76 us on the presenter and delaying
-// its pyramid build by 30 us per frame, and the pyramid build of the other rank running 39 us instead of 15 us next to its early-list push.
-// This kernel is built to be CO-RESIDENT with them: 64 threads, < 64 registers and 16 KB of shared memory per CTA (what the cull kernels
-// leave free on every SM), one CTA per SM.  MEASURED (2 GPUs, profiles/r02e_*): co-residency works -- the empty late-list push drops to 7-13 us
-// and delays nothing -- but the bulk stores share the SM's copy engine with the cull kernels' own TMA loads: the pyramid build next to a
-// push went 15 -> 31 us, the late pass 175 -> 197 us.  The default is therefore the register-store kernel above in the SAME small shape
-// (gather_push_kernel<64>, one CTA per SM: co-resident, and its stores do not queue with anybody's TMA loads); this one stays selectable.
-// A CTA walks 16-byte-aligned 8 KB chunks of the DESTINATION range: the chunk is loaded from the
-// local list into shared memory with plain 8-byte loads (24-byte records make the source only 8-byte aligned relative to the destination)
-// and leaves the SM as ONE bulk asynchronous store (cp.async.bulk.global.shared::cta) -- the copy engine of the SM, not its load/store
-// unit, waits for the link.  Two stages: the next chunk is loaded while the previous one drains.
-constexpr int kPushThreads = 64;
-constexpr uint32_t kPushChunk = 8192;            // bytes; multiple of 16
-constexpr int kPushStages = 2;
-
-__device__ __forceinline__ uint32_t push_smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
-__global__ void __launch_bounds__(kPushThreads) gather_push_tma_kernel(const GatherParams p)
-{
-    extern __shared__ __align__(128) unsigned char push_smem[];
-    __shared__ uint64_t s_off;
-    const uint32_t tid = threadIdx.x;
-    uint32_t count;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(count) : "l"(p.srcCount));
-    if (tid == 0) {
-        uint64_t* row = p.flags + (p.epoch % uint32_t(kEpochSlots)) * kFlagStride;
-        if (blockIdx.x == 0) {
-            if (p.epoch > 2u)                                              // back-pressure: everybody is done with epoch e - 2 (same half of the gather buffer)
-                for (uint32_t r = 0; r < p.world; ++r)
-                    while (int32_t(uint32_t(ld_acquire_sys_u64(p.flags + kDoneRow * kFlagStride + r)) - (p.epoch - 2u)) < 0) { }
-            st_release_sys_u64(row + p.rank, (uint64_t(p.epoch) << 32) | count);
-        }
-        uint64_t off = 0;
-        for (uint32_t r = 0; r < p.rank; ++r) {
-            uint64_t w;
-            do { w = ld_acquire_sys_u64(row + r); } while (uint32_t(w >> 32) != p.epoch);
-            off += uint32_t(w);
-        }
-        s_off = off;
-    }
-    __syncthreads();
-    const uint64_t off = s_off;
-    const uint64_t room = off < p.capacity ? p.capacity - off : 0ull;
-    const uint64_t nrec = room < count ? room : count;
-    const uint64_t bytes = nrec * p.recWords * 4ull;                       // multiple of 8
-    unsigned char* dst = reinterpret_cast<unsigned char*>(p.dst) + off * p.recWords * 4ull;     // 8-byte aligned
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.src);
-    // head / tail: the at most 8 bytes on either side of the 16-byte-aligned body go out as plain stores (CTA 0)
-    const uint64_t head = (bytes != 0ull && (reinterpret_cast<uintptr_t>(dst) & 15u) != 0u) ? 8ull : 0ull;
-    const uint64_t body = (bytes - head) & ~15ull;
-    if (blockIdx.x == 0 && tid == 0) {
-        if (head) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(src);
-        if (head + body < bytes) *reinterpret_cast<uint2*>(dst + head + body) = *reinterpret_cast<const uint2*>(src + head + body);
-    }
-    const uint64_t nChunks = (body + kPushChunk - 1) / kPushChunk;
-    uint32_t k = 0;                                                        // chunks this CTA has issued
-    for (uint64_t c = blockIdx.x; c < nChunks; c += gridDim.x, ++k) {
-        unsigned char* stage = push_smem + (k % uint32_t(kPushStages)) * kPushChunk;
-        if (k >= uint32_t(kPushStages)) {
-            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPushStages - 1) : "memory");   // the store that last used this stage has read it
-            __syncthreads();
-        }
-        const uint64_t b0 = c * kPushChunk;
-        const uint32_t len = uint32_t(body - b0 < kPushChunk ? body - b0 : kPushChunk);                        // multiple of 16
-        const uint2* s2 = reinterpret_cast<const uint2*>(src + head + b0);
-        uint2* d2 = reinterpret_cast<uint2*>(stage);
-        const uint32_t n8 = len >> 3;
-        uint32_t j = tid;
-        for (; j + 7u * kPushThreads < n8; j += 8u * kPushThreads) {
-            uint2 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = s2[j + uint32_t(u) * kPushThreads];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) d2[j + uint32_t(u) * kPushThreads] = v[u];
-        }
-        for (; j < n8; j += kPushThreads) d2[j] = s2[j];
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of shared memory -> visible to the bulk copy
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head + b0), "r"(push_smem_u32(stage)), "r"(len) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-    }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");    // every bulk store of this CTA has completed
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t prev = atomicAdd(p.done, 1u);
-        if (prev == gridDim.x - 1u) {
-            *p.done = 0u;
-            if (p.signalDone) st_release_sys_u64(p.flags + kDoneRow * kFlagStride + p.rank, uint64_t(p.epoch));
-        }
-    }
-}
+// A variant of this push that leaves the SM through TMA bulk stores (cp.async.bulk.global.shared::cta from a two-stage shared-memory ring) was built
+// and measured in round 2 (profiles/r02h_n8_ab.txt): co-residency worked the same, but the bulk stores share the SM's copy
+// engine with the cull kernels' own TMA loads (pyramid build next to a push 15 -> 31 us, late pass 175 -> 197 us).  Register stores stayed; the
+// variant and the round-1 256-thread shape (which cannot start next to the persistent cull kernels at all) were deleted.
 
 // Descriptor transport, presenter side.  The ranks shipped {objectId, absolute LOD id} (8 bytes) per record into the descriptor area of the gather
 // buffer, concatenated in rank order exactly like records; this kernel waits until every OTHER rank's push of `epoch` has landed (done flags; the
@@ -406,10 +314,8 @@ static int gather_launch(blz_cull_ctx* c, uint32_t epoch, cudaStream_t stream, i
     p.dst = desc ? descArea + size_t(epoch & 1u) * c->gatherCap * 2u : c->gatherDst + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords;
     p.capacity = c->gatherCap; p.rank = uint32_t(c->rank); p.world = uint32_t(c->world); p.epoch = epoch;
     p.signalDone = (desc && c->gatherOwner) ? 0u : 1u;
-    const int perSM = grid > 0 && grid < c->numSMs ? grid : c->numSMs;             // the co-resident forms: one small CTA per SM at most
-    if (c->optGatherTma == 1) gather_push_tma_kernel<<<perSM, kPushThreads, kPushStages * kPushChunk, stream>>>(p);
-    else if (c->optGatherTma == 2) gather_push_kernel<kPushThreads><<<perSM, kPushThreads, 0, stream>>>(p);
-    else gather_push_kernel<kGatherThreads><<<grid, kGatherThreads, 0, stream>>>(p);
+    const int perSM = grid > 0 && grid < c->numSMs ? grid : c->numSMs;             // one small co-resident CTA per SM at most
+    gather_push_kernel<<<perSM, kPushThreads, 0, stream>>>(p);
     CU_TRY(cudaGetLastError());
     c->launches++;
     return BLZ_OK;
@@ -448,7 +354,7 @@ int blz_cull_gather_push(blz_cull_ctx* c, uint32_t epoch)
     for (int k = 0; k < 2; ++k) if (c->evPushValid[k]) CU_TRY(cudaStreamWaitEvent(c->stream, c->evPush[k], 0));
     if (c->evExpandValid) CU_TRY(cudaStreamWaitEvent(c->stream, c->evExpand, 0));
     const bool expand = gather_desc_mode(c) && c->gatherOwner;
-    rc = gather_launch(c, epoch, c->stream, c->numSMs * 2); if (rc) return rc;
+    rc = gather_launch(c, epoch, c->stream, c->numSMs); if (rc) return rc;
     return expand ? gather_expand_launch(c, epoch, c->stream) : BLZ_OK;
 }
 
@@ -475,14 +381,8 @@ int blz_cull_gather_push_async(blz_cull_ctx* c, uint32_t epoch)
     // throttle themselves -- the list has the rest of the frame to arrive.  Measured at 8 GPUs (profiles/r02h_n8_ab.txt, ms per frame):
     // 148 CTAs 0.308 (pyramid next to the push 0.053 ms), 16 CTAs 0.290, 4 CTAs 0.746 (the push itself becomes the frame).
     static const int envCtas = [] { const char* e = getenv("BLZ_GATHER_CTAS"); return e ? atoi(e) : 0; }();
-    int ctas;
-    if (c->optGatherTma != 0) {
-        ctas = 224 / (c->world > 1 ? c->world - 1 : 1);
-        ctas = ctas < 16 ? 16 : (ctas > 64 ? 64 : ctas);
-    } else {
-        ctas = 56 / (c->world > 1 ? c->world - 1 : 1);                               // r01 kernel (256-thread CTAs): 8 CTAs at 8 GPUs
-        ctas = ctas < 4 ? 4 : (ctas > 32 ? 32 : ctas);
-    }
+    int ctas = 224 / (c->world > 1 ? c->world - 1 : 1);
+    ctas = ctas < 16 ? 16 : (ctas > 64 ? 64 : ctas);
     if (envCtas > 0) ctas = envCtas;
     const bool expand = gather_desc_mode(c) && c->gatherOwner;
     rc = gather_launch(c, epoch, c->gatherStream, ctas); if (rc) return rc;
