@@ -389,7 +389,7 @@ int blz_cull_synchronize(blz_cull_ctx* c)
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (c->gatherStream) CU_TRY(cudaStreamSynchronize(c->gatherStream));
-    return BLZ_OK;
+    return gather_report_timeout(c);
 }
 
 namespace {
@@ -866,6 +866,7 @@ int blz_cull_set_option(blz_cull_ctx* c, const char* name, int64_t value)
     if (strcmp(name, "early_auto") == 0) { c->optEarlyAuto = value; c->earlyDense = false; return BLZ_OK; }
     if (strcmp(name, "stream_cfg") == 0) { c->optStreamCfg = value; return BLZ_OK; }
     if (strcmp(name, "gather_desc") == 0) { c->optGatherDesc = value; return BLZ_OK; }
+    if (strcmp(name, "gather_timeout_ms") == 0) { if (value < 0) return fail(BLZ_ERR_INVALID, "gather_timeout_ms < 0"); c->optGatherTimeoutMs = value; return BLZ_OK; }
     if (strcmp(name, "validate_scene") == 0) { c->optValidate = value; return BLZ_OK; }
     if (strcmp(name, "epoch_wrap_at") == 0) { if (value < 4) return fail(BLZ_ERR_INVALID, "epoch_wrap_at < 4"); c->epochWrapAt = uint32_t(value); return BLZ_OK; }   // tests: restart the status tag every `value` launches
     return fail(BLZ_ERR_INVALID, "unknown option '%s'", name);

@@ -9,6 +9,7 @@
 // blob at set-up time (blitzen_b200/dist.py).
 #include "ctx.h"
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -35,6 +36,46 @@ __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p)
     return v;
 }
 
+// Device-side waits are bounded: a rank that never arrives (a crashed process, a protocol error) must turn into an error code on the host, not
+// into kernels that spin for ever on every other GPU of the box.  Each waiting thread reads %globaltimer every 64 polls; when the kernel has waited
+// longer than the budget in total it records {what, epoch, peer} in a host-mapped word block, sets the context's sticky device word (so that every
+// later gather kernel of this context skips its waits instead of paying the budget again), moves no data, and still raises its flags so that the
+// timeout does not cascade as a hang.  The host reports BLZ_ERR_TIMEOUT from the next call that synchronises (blz_cull_synchronize,
+// blz_cull_gather_read, blz_cull_consume_gathered).  Option "gather_timeout_ms" (default 10 000; 0 = wait for ever).
+enum : uint32_t { kWaitCount = 1u, kWaitBackPressure = 2u, kWaitExpand = 3u, kWaitRead = 4u };
+struct SpinGuard {
+    uint32_t* sticky; volatile uint32_t* host; uint64_t budgetNs, t0; uint32_t epoch; bool dead;
+    __device__ __forceinline__ void begin(uint32_t* stickyWord, uint32_t* hostWords, uint64_t budget, uint32_t e)
+    {
+        sticky = stickyWord; host = hostWords; budgetNs = budget; epoch = e;
+        uint32_t v;
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(stickyWord));
+        dead = v != 0u;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    }
+    __device__ __forceinline__ bool expired(uint32_t what, uint32_t peer)
+    {
+        if (budgetNs == 0ull) return false;
+        uint64_t t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 <= budgetNs) return false;
+        dead = true;
+        if (atomicExch(sticky, 1u) == 0u) { host[1] = epoch; host[2] = peer; __threadfence_system(); host[0] = what; __threadfence_system(); }
+        return true;
+    }
+};
+// polls *word until ok(value); false = gave up (budget spent now or earlier)
+template <class Ok>
+__device__ __forceinline__ bool spin_until(const uint64_t* word, Ok ok, uint64_t& value, SpinGuard& g, uint32_t what, uint32_t peer)
+{
+    if (g.dead) return false;
+    for (uint32_t polls = 1u;; ++polls) {
+        value = ld_acquire_sys_u64(word);
+        if (ok(value)) return true;
+        if ((polls & 63u) == 0u && g.expired(what, peer)) return false;
+    }
+}
+
 struct GatherParams {
     const uint32_t* src; const uint32_t* srcCount;   // this rank's compacted list (device-local)
     uint32_t* dst; uint64_t* flags;                  // presenter's buffer + flag block (peer-mapped, or local on the presenter)
@@ -42,6 +83,7 @@ struct GatherParams {
     uint64_t capacity;                               // records the presenter's buffer holds
     uint32_t recWords, rank, world, epoch;
     uint32_t signalDone;                             // 0 on the presenter in descriptor mode: its done flag is raised by gather_expand_kernel
+    uint32_t* sticky; uint32_t* errHost; uint64_t timeoutNs;   // bounded waits (SpinGuard)
 };
 
 // 64 threads, 32 registers, no shared memory to speak of: at most one CTA per SM, which fits in what the persistent cull kernels leave free
@@ -54,20 +96,20 @@ __global__ void __launch_bounds__(kPushThreads) gather_push_kernel(const GatherP
     uint32_t count;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(count) : "l"(p.srcCount));
     if (tid == 0) {
+        SpinGuard g; g.begin(p.sticky, p.errHost, p.timeoutNs, p.epoch);
         uint64_t* row = p.flags + (p.epoch % uint32_t(kEpochSlots)) * kFlagStride;
+        uint64_t w;
         if (blockIdx.x == 0) {
             if (p.epoch > 2u)                                              // back-pressure: everybody is done with epoch e - 2 (same half of the gather buffer)
                 for (uint32_t r = 0; r < p.world; ++r)
-                    while (int32_t(uint32_t(ld_acquire_sys_u64(p.flags + kDoneRow * kFlagStride + r)) - (p.epoch - 2u)) < 0) { }
+                    spin_until(p.flags + kDoneRow * kFlagStride + r, [&](uint64_t v) { return int32_t(uint32_t(v) - (p.epoch - 2u)) >= 0; }, w, g, kWaitBackPressure, r);
             st_release_sys_u64(row + p.rank, (uint64_t(p.epoch) << 32) | count);
         }
         uint64_t off = 0;
         for (uint32_t r = 0; r < p.rank; ++r) {
-            uint64_t w;
-            do { w = ld_acquire_sys_u64(row + r); } while (uint32_t(w >> 32) != p.epoch);
-            off += uint32_t(w);
+            if (spin_until(row + r, [&](uint64_t v) { return uint32_t(v >> 32) == p.epoch; }, w, g, kWaitCount, r)) off += uint32_t(w);
         }
-        s_off = off;
+        s_off = g.dead ? ~0ull : off;                                      // gave up: nothing is moved (room = 0 below), the flags are still raised
     }
     __syncthreads();
     const uint64_t off = s_off;
@@ -120,6 +162,7 @@ __global__ void __launch_bounds__(kPushThreads) gather_push_kernel(const GatherP
 struct ExpandParams {
     const uint2* descs; uint32_t* records; uint64_t* flags; const LodData* lods; uint32_t* done; uint32_t lodCount;
     uint64_t capacity; uint32_t recWords, world, rank, epoch;
+    uint32_t* sticky; uint32_t* errHost; uint64_t timeoutNs;
 };
 constexpr int kExpandThreads = 64;
 constexpr int kExpandInFlight = 8;
@@ -142,12 +185,13 @@ __global__ void __launch_bounds__(kExpandThreads) gather_expand_kernel(const Exp
     constexpr int kInFlight = RECW2 == 3 ? kExpandInFlight : kExpandInFlight - 2;    // DX32: 6, which keeps the kernel at 32 registers like the VK24 form
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
-        uint64_t total = 0;
+        SpinGuard g; g.begin(p.sticky, p.errHost, p.timeoutNs, p.epoch);
+        uint64_t total = 0, w;
         for (uint32_t r = 0; r < p.world; ++r) {
-            if (r != p.rank) while (int32_t(uint32_t(ld_acquire_sys_u64(p.flags + kDoneRow * kFlagStride + r)) - p.epoch) < 0) { }
+            if (r != p.rank) spin_until(p.flags + kDoneRow * kFlagStride + r, [&](uint64_t v) { return int32_t(uint32_t(v) - p.epoch) >= 0; }, w, g, kWaitExpand, r);
             total += uint32_t(ld_acquire_sys_u64(p.flags + (p.epoch % uint32_t(kEpochSlots)) * kFlagStride + r));
         }
-        s_total = total < p.capacity ? total : p.capacity;
+        s_total = g.dead ? 0ull : (total < p.capacity ? total : p.capacity);
     }
     __syncthreads();
     const uint64_t n = s_total;
@@ -181,10 +225,14 @@ __global__ void __launch_bounds__(kExpandThreads) gather_expand_kernel(const Exp
     }
 }
 
-__global__ void gather_wait_kernel(const uint64_t* flags, uint32_t world, uint32_t epoch)
+__global__ void gather_wait_kernel(const uint64_t* flags, uint32_t world, uint32_t epoch, uint32_t* sticky, uint32_t* errHost, uint64_t timeoutNs)
 {
     const uint32_t r = threadIdx.x;
-    if (r < world) { while (int32_t(uint32_t(ld_acquire_sys_u64(flags + kDoneRow * kFlagStride + r)) - epoch) < 0) { } }
+    if (r < world) {
+        SpinGuard g; g.begin(sticky, errHost, timeoutNs, epoch);
+        uint64_t w;
+        spin_until(flags + kDoneRow * kFlagStride + r, [&](uint64_t v) { return int32_t(uint32_t(v) - epoch) >= 0; }, w, g, kWaitRead, r);
+    }
 }
 
 // Instance-list gather (indirect instancing, objects sharded by contiguous ranges): the bucket of LOD l on the presenter is the concatenation of
@@ -236,9 +284,27 @@ void gather_release(blz_cull_ctx* c)
     if (c->instDstMapped && c->instDst) cudaIpcCloseMemHandle(c->instDst);
     c->instDst = nullptr; c->instDstMapped = false;
     if (c->gatherDone) cudaFree(c->gatherDone);
+    if (c->gatherErrHost) { cudaFreeHost(c->gatherErrHost); c->gatherErrHost = nullptr; c->gatherErrDev = nullptr; }
     if (c->gatherStream) { cudaStreamSynchronize(c->gatherStream); cudaStreamDestroy(c->gatherStream); cudaEventDestroy(c->evCull); cudaEventDestroy(c->evPush[0]); cudaEventDestroy(c->evPush[1]); cudaEventDestroy(c->evExpand); c->evExpandValid = false; c->gatherStream = nullptr; c->evPushValid[0] = c->evPushValid[1] = false; }
     c->gatherBuf = nullptr; c->gatherFlags = nullptr; c->gatherDst = nullptr; c->gatherDstFlags = nullptr; c->gatherDone = nullptr;
     c->gatherOwner = c->gatherImported = c->gatherPeerMapped = false;
+}
+
+// Called behind a host synchronisation: turns a device-side wait that gave up into BLZ_ERR_TIMEOUT (once) and re-arms the waits.  The ranks'
+// epochs no longer agree after a timeout: the gather has to be set up again (export / import) before it is used further; the context stays usable.
+int gather_report_timeout(blz_cull_ctx* c)
+{
+    if (!c->gatherErrHost) return BLZ_OK;
+    volatile uint32_t* h = c->gatherErrHost;
+    const uint32_t what = h[0];
+    if (what == 0u) return BLZ_OK;
+    const uint32_t epoch = h[1], peer = h[2];
+    h[0] = 0u;
+    cudaMemset(c->gatherDone + 2, 0, sizeof(uint32_t));
+    static const char* const names[] = { "?", "rank %u's record count of epoch %u", "rank %u to finish with epoch %u - 2 (back-pressure)", "rank %u's push of epoch %u (expansion)", "rank %u's push of epoch %u (read)" };
+    char what_s[160];
+    snprintf(what_s, sizeof what_s, names[what <= 4u ? what : 0u], peer, epoch);
+    return fail(BLZ_ERR_TIMEOUT, "draw-list gather: rank %d waited more than %lld ms on the device for %s; nothing was moved for that push -- set the gather up again on every rank", c->rank, (long long)c->optGatherTimeoutMs, what_s);
 }
 
 } // namespace blz
@@ -287,8 +353,11 @@ int blz_cull_gather_import(blz_cull_ctx* c, const void* blob128, int rank, int w
         c->gatherDst = static_cast<uint32_t*>(a); c->gatherDstFlags = static_cast<uint64_t*>(b); c->gatherPeerMapped = true;
     }
     if (!c->gatherDone) {
-        CU_TRY(cudaMalloc(&c->gatherDone, 2 * sizeof(uint32_t)));          // CTA-completion counters: [0] push, [1] expansion (self-resetting)
-        CU_TRY(cudaMemset(c->gatherDone, 0, 2 * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&c->gatherDone, 4 * sizeof(uint32_t)));          // CTA-completion counters: [0] push, [1] expansion (self-resetting); [2] sticky "a wait timed out" word
+        CU_TRY(cudaMemset(c->gatherDone, 0, 4 * sizeof(uint32_t)));
+        CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->gatherErrHost), 4 * sizeof(uint32_t), cudaHostAllocMapped));
+        memset(c->gatherErrHost, 0, 4 * sizeof(uint32_t));
+        CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->gatherErrDev), c->gatherErrHost, 0));
     }
     c->gatherImported = true;
     return BLZ_OK;
@@ -314,6 +383,7 @@ static int gather_launch(blz_cull_ctx* c, uint32_t epoch, cudaStream_t stream, i
     p.dst = desc ? descArea + size_t(epoch & 1u) * c->gatherCap * 2u : c->gatherDst + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords;
     p.capacity = c->gatherCap; p.rank = uint32_t(c->rank); p.world = uint32_t(c->world); p.epoch = epoch;
     p.signalDone = (desc && c->gatherOwner) ? 0u : 1u;
+    p.sticky = c->gatherDone + 2; p.errHost = c->gatherErrDev; p.timeoutNs = uint64_t(c->optGatherTimeoutMs) * 1000000ull;
     const int perSM = grid > 0 && grid < c->numSMs ? grid : c->numSMs;             // one small co-resident CTA per SM at most
     gather_push_kernel<<<perSM, kPushThreads, 0, stream>>>(p);
     CU_TRY(cudaGetLastError());
@@ -329,6 +399,7 @@ static int gather_expand_launch(blz_cull_ctx* c, uint32_t epoch, cudaStream_t st
     e.records = c->gatherBuf + size_t(epoch & 1u) * c->gatherCap * c->gatherRecWords;
     e.flags = c->gatherFlags; e.lods = c->lods; e.lodCount = c->nLods; e.capacity = c->gatherCap; e.recWords = c->gatherRecWords;
     e.done = c->gatherDone + 1; e.world = uint32_t(c->world); e.rank = uint32_t(c->rank); e.epoch = epoch;
+    e.sticky = c->gatherDone + 2; e.errHost = c->gatherErrDev; e.timeoutNs = uint64_t(c->optGatherTimeoutMs) * 1000000ull;
     static const int envCtas = [] { const char* v = getenv("BLZ_EXPAND_CTAS"); return v ? atoi(v) : 0; }();   // measurement aid
     const int grid = envCtas > 0 && envCtas < c->numSMs ? envCtas : c->numSMs;                                // one small co-resident CTA per SM at most
     if (c->gatherRecWords == 6u) gather_expand_kernel<3><<<grid, kExpandThreads, 0, stream>>>(e);
@@ -420,12 +491,13 @@ int blz_cull_gather_read(blz_cull_ctx* c, uint32_t epoch, void* recordsHost, uin
     if (!c || !c->gatherOwner) return fail(BLZ_ERR_INVALID, "only the presenting rank (the exporter) can read the gathered list");
     CU_TRY(cudaSetDevice(c->device));
     if (c->evExpandValid) CU_TRY(cudaStreamWaitEvent(c->stream, c->evExpand, 0));   // asynchronous pushes in descriptor mode: the expansion runs on the side stream
-    gather_wait_kernel<<<1, kFlagStride, 0, c->stream>>>(c->gatherFlags, uint32_t(c->world), epoch);
+    gather_wait_kernel<<<1, kFlagStride, 0, c->stream>>>(c->gatherFlags, uint32_t(c->world), epoch, c->gatherDone + 2, c->gatherErrDev, uint64_t(c->optGatherTimeoutMs) * 1000000ull);
     CU_TRY(cudaGetLastError());
     c->launches++;
     uint64_t flags[kFlagStride];
     CU_TRY(cudaMemcpyAsync(flags, c->gatherFlags + (epoch % uint32_t(kEpochSlots)) * kFlagStride, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    { const int trc = gather_report_timeout(c); if (trc) return trc; }
     uint64_t total = 0;
     for (int r = 0; r < c->world; ++r) { if (outCounts) outCounts[r] = uint32_t(flags[r]); total += uint32_t(flags[r]); }
     if (total > c->gatherCap) total = c->gatherCap;

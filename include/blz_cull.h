@@ -41,7 +41,8 @@ typedef enum blz_status {
     BLZ_ERR_CUDA = -2,         /* CUDA runtime error (no device, launch failure, out of memory) */
     BLZ_ERR_CAPACITY = -3,     /* a fixed internal capacity would be exceeded (tables too large, ...) */
     BLZ_ERR_UNSUPPORTED = -4,
-    BLZ_ERR_STATE = -5         /* the call needs something an earlier call sets up (scene, export, fence) */
+    BLZ_ERR_STATE = -5,        /* the call needs something an earlier call sets up (scene, export, fence) */
+    BLZ_ERR_TIMEOUT = -6       /* multi-GPU gather: a peer did not arrive within the device-side wait budget (option "gather_timeout_ms") */
 } blz_status;
 
 /* which render-object list a pass runs over: the reference keeps three (Resources/RenderObject/blitRender.h:14-21) and
@@ -211,7 +212,11 @@ int blz_cull_consume_gathered(blz_cull_ctx* ctx, uint32_t epoch, blz_consume_sum
  *   LOD table into the same record area, behind its own push -- a third of the bytes into the one GPU that ingests everything; the
  *   gathered list is byte-identical either way and is complete once every rank's done flag carries the epoch (the presenter raises its
  *   own after the expansion: blz_cull_gather_read / blz_cull_consume_gathered / blz_cull_gather_join wait for it).  Cluster draw lists
- *   always travel as records. */
+ *   always travel as records.
+ *   Failure detection: every device-side wait of the gather is bounded (option "gather_timeout_ms", default 10 000, 0 = for ever).  A rank
+ *   whose peer never arrives moves nothing for that push, still raises its own flags (the timeout does not cascade as a hang) and the next
+ *   call that synchronises -- blz_cull_synchronize, blz_cull_gather_read, blz_cull_consume_gathered -- returns BLZ_ERR_TIMEOUT naming the
+ *   peer and the epoch; the gather must then be set up again on every rank, the context itself stays usable. */
 int blz_cull_gather_export(blz_cull_ctx* ctx, uint64_t capacity_records, int record_format, void* out_blob128);
 int blz_cull_gather_import(blz_cull_ctx* ctx, const void* presenter_blob128, int rank, int world);
 /* ranks that did not export learn the presenter buffer's capacity / record format from the host layer */

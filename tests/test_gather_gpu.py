@@ -69,3 +69,35 @@ def test_gather_sync_and_async_single_rank(capi, small_scene, desc, fmt_name):
         ctx.gather_join()
         gotE, _ = ctx.gather_read(4, 1, fmt)
         assert np.array_equal(recs_u32(gotE), e2)
+
+
+@pytest.mark.parametrize("desc", [1, 0], ids=["descriptors", "records"])
+def test_absent_peer_times_out_instead_of_hanging(capi, small_scene, desc):
+    """Failure detection: this context plays rank 1 of 2 and nobody plays rank 0, so its push waits on the device for rank 0's record count.
+    The wait is bounded (option gather_timeout_ms): the kernels end, the next synchronising call reports BLZ_ERR_TIMEOUT naming the peer
+    and the epoch, and the context stays usable (a fresh gather set-up works again)."""
+    import time
+    sc = small_scene
+    n = len(sc["objs"])
+    view = view_at(position=(380, 380, 380), z_far=2000.0)
+    with capi.CullContext(0) as ctx:
+        ctx.upload_scene(sc["objs"], sc["transforms"], sc["surfaces"], sc["lods"])
+        ctx.set_view(view)
+        ctx.set_option("gather_desc", desc)
+        ctx.set_option("gather_timeout_ms", 200)
+        ctx.gather_export(n, capi.REC_VK24)
+        ctx.gather_import(None, 1, 2, n, capi.REC_VK24)          # the exporter writes through its own pointers whatever its rank
+        ctx.frustum_lod()
+        expect, _ = ctx.read_draws()
+        t0 = time.time()
+        ctx.gather_push(1)
+        with pytest.raises(capi.BlzError, match=r"error -6.*rank 0"):
+            ctx.synchronize()
+        assert time.time() - t0 < 5.0
+        ctx.synchronize()                                          # reported once; the context is usable again
+        # a later push of the same (broken) set-up does not pay the budget again before it has been reported ... and a fresh set-up works
+        ctx.gather_export(n, capi.REC_VK24)
+        ctx.gather_import(None, 0, 1, n, capi.REC_VK24)
+        ctx.frustum_lod(); ctx.gather_push(1)
+        got, counts = ctx.gather_read(1, 1)
+        assert counts[0] == len(expect) and np.array_equal(recs_u32(got), recs_u32(expect))
