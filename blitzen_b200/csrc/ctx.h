@@ -67,7 +67,7 @@ struct blz_cull_ctx {
     uint32_t* gatherBuf = nullptr; uint64_t gatherCap = 0; uint32_t gatherRecWords = 6; uint64_t* gatherFlags = nullptr; bool gatherOwner = false;
     uint32_t* gatherDst = nullptr; uint64_t* gatherDstFlags = nullptr; int rank = 0, world = 1; bool gatherImported = false, gatherPeerMapped = false;
     uint32_t* gatherDone = nullptr;
-    uint32_t* gatherErrHost = nullptr; uint32_t* gatherErrDev = nullptr; int64_t optGatherTimeoutMs = 10000;   // bounded device-side waits (gather.cu: SpinGuard)
+    uint32_t* gatherErrHost = nullptr; uint32_t* gatherErrDev = nullptr; int64_t optGatherTimeoutMs = 60000;   // bounded device-side waits (gather.cu: SpinGuard)
     uint32_t* instDst = nullptr; bool instDstMapped = false;   // presenter's instance index buffer (instance-list gather)
     // descriptor transport (gather.cu): the draw passes also write {objectId, lodId} per record; the ranks ship those 8 bytes instead of the 24/32-byte
     // records and the presenter expands them with its own LOD table.  descs / descsAlt flip together with draws / drawsAlt.

@@ -41,7 +41,7 @@ __device__ __forceinline__ uint64_t ld_acquire_sys_u64(const uint64_t* p)
 // longer than the budget in total it records {what, epoch, peer} in a host-mapped word block, sets the context's sticky device word (so that every
 // later gather kernel of this context skips its waits instead of paying the budget again), moves no data, and still raises its flags so that the
 // timeout does not cascade as a hang.  The host reports BLZ_ERR_TIMEOUT from the next call that synchronises (blz_cull_synchronize,
-// blz_cull_gather_read, blz_cull_consume_gathered).  Option "gather_timeout_ms" (default 10 000; 0 = wait for ever).
+// blz_cull_gather_read, blz_cull_consume_gathered).  Option "gather_timeout_ms" (default 60 000: generous, a false alarm costs a run; 0 = wait for ever).
 enum : uint32_t { kWaitCount = 1u, kWaitBackPressure = 2u, kWaitExpand = 3u, kWaitRead = 4u };
 struct SpinGuard {
     uint32_t* sticky; volatile uint32_t* host; uint64_t budgetNs, t0; uint32_t epoch; bool dead;

@@ -213,7 +213,7 @@ int blz_cull_consume_gathered(blz_cull_ctx* ctx, uint32_t epoch, blz_consume_sum
  *   gathered list is byte-identical either way and is complete once every rank's done flag carries the epoch (the presenter raises its
  *   own after the expansion: blz_cull_gather_read / blz_cull_consume_gathered / blz_cull_gather_join wait for it).  Cluster draw lists
  *   always travel as records.
- *   Failure detection: every device-side wait of the gather is bounded (option "gather_timeout_ms", default 10 000, 0 = for ever).  A rank
+ *   Failure detection: every device-side wait of the gather is bounded (option "gather_timeout_ms", default 60 000, 0 = for ever).  A rank
  *   whose peer never arrives moves nothing for that push, still raises its own flags (the timeout does not cascade as a hang) and the next
  *   call that synchronises -- blz_cull_synchronize, blz_cull_gather_read, blz_cull_consume_gathered -- returns BLZ_ERR_TIMEOUT naming the
  *   peer and the epoch; the gather must then be set up again on every rank, the context itself stays usable. */
